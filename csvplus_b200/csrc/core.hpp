@@ -1,0 +1,179 @@
+// core.hpp — host-side internals shared by the C-ABI translation units:
+// context (device, stream, stream-ordered pool), refcounted device buffers, string columns,
+// tables, indices, error helpers and per-kernel timing records.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/csvplus_b200.h"
+
+namespace cpb {
+
+struct Ctx;
+
+// ------------------------------------------------------------------ errors
+struct CudaFail { cudaError_t e; const char* what; const char* file; int line; };
+#define CPB_CUDA(x)                                                        \
+    do {                                                                   \
+        cudaError_t _e = (x);                                              \
+        if (_e != cudaSuccess) throw ::cpb::CudaFail{_e, #x, __FILE__, __LINE__}; \
+    } while (0)
+
+struct DataError {  // reference-visible error (cpb_error payload)
+    int kind; int column_index; uint64_t line; bool has_line; std::string msg;
+};
+struct ArgError { int status; std::string msg; };
+
+inline void fill_error(cpb_error* e, int kind, int col, uint64_t line, bool has_line, const std::string& msg) {
+    if (!e) return;
+    e->kind = kind; e->column_index = col; e->line = line; e->has_line = has_line ? 1 : 0; e->_pad = 0;
+    size_t n = msg.size() < sizeof(e->msg) - 1 ? msg.size() : sizeof(e->msg) - 1;
+    memcpy(e->msg, msg.data(), n); e->msg[n] = 0;
+}
+inline void clear_error(cpb_error* e) { if (e) { memset(e, 0, sizeof(*e)); e->column_index = -1; } }
+
+// Go's %q for the plain names csvplus prints (csvplus.go:129, :725, :1128, :1179)
+std::string go_quote(const std::string& s);
+
+// ------------------------------------------------------------------ device memory
+struct DevBuf {  // stream-ordered allocation owned by a ctx
+    Ctx* ctx = nullptr; void* p = nullptr; size_t n = 0;
+    DevBuf(Ctx* c, size_t bytes);
+    ~DevBuf();
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+using Buf = std::shared_ptr<DevBuf>;
+
+// Arrow-style string column: value i = data[offsets[i] .. offsets[i+1]); offsets are uint32 (a
+// column of one table/batch holds < 4 GiB of bytes — DESIGN.md "batches").  `row0` lets row-range
+// views (Top/Drop/Find/SubIndex) share the buffers.
+struct Column {
+    std::string name;
+    Buf offsets;      // uint32[nrows_alloc+1]
+    Buf data;         // uint8[]
+    int64_t row0 = 0; // first row of this view inside `offsets`
+    const uint32_t* off() const { return offsets->as<uint32_t>() + row0; }
+    const uint8_t* bytes() const { return data ? data->as<uint8_t>() : nullptr; }
+};
+
+struct Table {
+    Ctx* ctx = nullptr;
+    int64_t nrows = 0;
+    uint64_t first_line = 0;  // DataSourceError.Line the source reports for row 0 (csvplus.go:1137 / :243)
+    std::vector<Column> cols;
+    int find(const std::string& name) const {
+        for (size_t i = 0; i < cols.size(); i++) if (cols[i].name == name) return (int)i;
+        return -1;
+    }
+};
+
+// csvplus Index (csvplus.go:610-614, :785-788): rows sorted on `key_cols`.  `table` holds the
+// rows physically in sorted order.  `image` is the order-preserving fixed-width key image
+// (sort.cu) of the sorted rows; `hash*` is the probe table over distinct full keys / key prefixes.
+struct HashTable {
+    int nkeys = 0;           // number of leading key columns hashed
+    uint32_t pbytes = 0;     // image bytes those columns cover
+    uint64_t nslots = 0;     // power of two
+    uint64_t nheads = 0;     // distinct key prefixes
+    Buf slots;               // uint32 head ordinal or 0xFFFFFFFF (open addressing, linear probing)
+    Buf heads;               // uint32[nheads+1]: sorted position of each distinct prefix; heads[nheads] = nrows
+};
+struct Index {
+    Ctx* ctx = nullptr;
+    std::shared_ptr<Table> table;      // sorted rows
+    std::vector<std::string> key_cols; // index.impl.columns
+    std::vector<int> key_col_idx;      // positions in table->cols
+    std::vector<uint32_t> key_width;   // per key column: max value length (bytes) in this index
+    uint32_t image_words = 0;          // uint64 words per row of the key image
+    Buf image;                         // uint64[image_words][nrows] (word-major / SoA)
+    std::map<int, HashTable> hash;     // by number of leading key columns
+};
+
+// ------------------------------------------------------------------ kernel stats
+struct KStat { uint64_t launches = 0; double ms = 0; uint64_t bytes = 0; };
+struct PendingEvent { std::string name; cudaEvent_t a, b; uint64_t bytes; };
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    std::mutex mu;              // one call in flight per ctx
+    std::string last_error;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    // stats
+    bool stats_on = false;
+    std::map<std::string, KStat> stats;
+    std::vector<PendingEvent> pending;
+    uint64_t launches = 0;
+    // small pinned scratch for D2H of results
+    void* pinned = nullptr; size_t pinned_n = 0;
+
+    void* pinned_scratch(size_t n);
+    void drain_events();
+};
+
+// RAII: time a kernel (or a group of launches) on the ctx stream when stats are enabled
+struct KernelTimer {
+    Ctx* c; bool on; cudaEvent_t a{}, b{}; std::string name; uint64_t bytes; int nlaunch;
+    KernelTimer(Ctx* ctx, const char* nm, uint64_t algo_bytes, int launches = 1);
+    ~KernelTimer();
+};
+
+struct DeviceGuard {  // every entry point: select device, serialise on the ctx
+    std::unique_lock<std::mutex> lk;
+    explicit DeviceGuard(Ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
+};
+
+inline Buf dev_alloc(Ctx* c, size_t bytes) { return std::make_shared<DevBuf>(c, bytes ? bytes : 1); }
+
+inline std::string to_string(cpb_str s) { return std::string(s.ptr ? s.ptr : "", (size_t)s.len); }
+
+// exception -> status translation used by every extern "C" body
+int translate_exception(Ctx* c, cpb_error* err);
+#define CPB_TRY(ctx, err) try {
+#define CPB_CATCH(ctx, err) } catch (...) { return ::cpb::translate_exception(ctx, err); }
+
+// ------------------------------------------------------------------ cross-TU operations
+// parse.cu
+std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* dev_bytes, uint64_t n, const cpb_reader_opts& o,
+                                 const std::vector<std::pair<std::string, int>>& spec, const cpb_pred* filter,
+                                 bool* had_error, DataError* derr);
+// gather.cu
+void exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, uint64_t n, uint64_t* total_dev);  // out[n] = total
+Column gather_column(Ctx* c, const Column& src, const uint32_t* row_ids, int64_t nout);
+std::shared_ptr<Table> gather_rows(Ctx* c, const Table& t, const uint32_t* row_ids, int64_t nout);
+std::shared_ptr<Table> filter_table(Ctx* c, const Table& t, const cpb_pred* pred);
+Column materialize(Ctx* c, const Column& col, int64_t nrows);  // view -> own compact buffers
+std::shared_ptr<Table> concat_tables(Ctx* c, const std::vector<const Table*>& parts);
+// sort.cu
+std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std::string>& keys, bool unique,
+                                   DataError* derr, bool* failed);
+uint32_t prefix_bytes(const Index& ix, int nk);  // image bytes covered by the first nk key columns
+Buf pack_with_widths(Ctx* c, const Table& t, const std::vector<int>& kidx, const std::vector<uint32_t>& width, uint32_t* words_out);
+// join.cu
+std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const std::vector<std::string>& cols,
+                                   bool anti, DataError* derr, bool* failed);
+void find_range(Ctx* c, Index& ix, const std::vector<std::string>& values, int64_t* lo, int64_t* hi);
+void index_dup_groups(Ctx* c, Index& ix, std::vector<int64_t>& lo, std::vector<int64_t>& hi);
+void index_dedup_apply(Ctx* c, Index& ix, const std::vector<int64_t>& keep, bool bug_compatible);
+// write.cu
+Buf table_to_csv(Ctx* c, const Table& t, const std::vector<int>& cols, const std::vector<std::string>& names,
+                 uint64_t* nbytes);
+
+}  // namespace cpb
+
+// opaque handle layouts of the C ABI
+struct cpb_ctx { cpb::Ctx c; };
+struct cpb_table { std::shared_ptr<cpb::Table> t; };
+struct cpb_index { std::shared_ptr<cpb::Index> ix; };

@@ -1,0 +1,295 @@
+// join.cu — K8/K9 of SURVEY §2: the probe side of DataSource.Join / Except and Index.Find.
+//
+// Replaces (reference): Join csvplus.go:545-569 (per probe row: SelectValues, indexImpl.first =
+// sort.Search lower bound :893-897 with cmp :907-920, then a forward scan while equal), mergeRows
+// :571-583, Except :588-608 (indexImpl.has :899-905) and indexImpl.find :870-891.
+//
+// The index keeps its sorted key image (sort.cu).  For a join on the first nk key columns the
+// distinct nk-column prefixes ("heads") of the sorted image are inserted into an open-addressing
+// hash table that maps a prefix to its run [heads[j], heads[j+1]) of sorted rows — exactly the
+// [lower_bound, upper_bound) range the reference finds by binary search, so output order (probe
+// order, then index order) is unchanged.  Small tables are staged into shared memory per CTA; large
+// ones are probed in L2/HBM.  Probe keys are packed with the index's column widths so equality of
+// images is equality of keys.
+#include <algorithm>
+
+#include "core.hpp"
+#include "util.cuh"
+
+namespace cpb {
+
+static inline uint32_t nblk(uint64_t n, int t) { return (uint32_t)((n + t - 1) / t); }
+constexpr uint32_t EMPTY = 0xffffffffu;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+    return h;
+}
+__device__ __forceinline__ uint64_t hash_prefix(const uint64_t* img, uint64_t n, uint64_t r, uint32_t pbytes) {
+    uint32_t full = pbytes >> 3, rem = pbytes & 7;
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint32_t w = 0; w < full; w++) h = mix64(h ^ img[(uint64_t)w * n + r]);
+    if (rem) h = mix64(h ^ (img[(uint64_t)full * n + r] & (~0ull << (8 * (8 - rem)))));
+    return h;
+}
+__device__ __forceinline__ bool prefix_equal2(const uint64_t* a, uint64_t na, uint64_t ra, const uint64_t* b, uint64_t nb, uint64_t rb,
+                                              uint32_t pbytes) {
+    uint32_t full = pbytes >> 3, rem = pbytes & 7;
+    for (uint32_t w = 0; w < full; w++) if (a[(uint64_t)w * na + ra] != b[(uint64_t)w * nb + rb]) return false;
+    if (rem) {
+        uint64_t m = ~0ull << (8 * (8 - rem));
+        if ((a[(uint64_t)full * na + ra] & m) != (b[(uint64_t)full * nb + rb] & m)) return false;
+    }
+    return true;
+}
+
+__global__ void head_flags2_kernel(const uint64_t* __restrict__ image, uint64_t n, uint32_t pbytes, uint32_t* head) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || !prefix_equal2(image, n, i, image, n, i - 1, pbytes)) ? 1u : 0u;
+}
+__global__ void compact_heads_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, uint32_t* out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) out[pos[i]] = (uint32_t)i;
+    if (i == 0) out[pos[n]] = (uint32_t)n;  // sentinel: heads[nheads] = nrows
+}
+__global__ void hash_insert_kernel(const uint64_t* __restrict__ image, uint64_t n, uint32_t pbytes, const uint32_t* __restrict__ heads,
+                                   uint64_t nheads, uint32_t* slots, uint64_t mask) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nheads) return;
+    uint64_t s = hash_prefix(image, n, heads[j], pbytes) & mask;
+    for (;;) {
+        uint32_t old = atomicCAS(&slots[s], EMPTY, (uint32_t)j);
+        if (old == EMPTY) return;
+        s = (s + 1) & mask;
+    }
+}
+
+// probe: per probe row the matching run of sorted index rows: lo[i], cnt[i] (cnt 0 = no match)
+template <bool SMEM>
+__global__ void __launch_bounds__(256) join_probe_kernel(const uint64_t* __restrict__ pimg, uint64_t np, const uint64_t* __restrict__ iimg,
+                                                         uint64_t ni, uint32_t pbytes, const uint32_t* __restrict__ slots_g, uint64_t nslots,
+                                                         const uint32_t* __restrict__ heads_g, uint64_t nheads, uint32_t* lo, uint32_t* cnt) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t* slots = slots_g;
+    const uint32_t* heads = heads_g;
+    if (SMEM) {  // stage the build-side table (slots + heads) into shared memory once per CTA
+        for (uint64_t i = threadIdx.x; i < nslots; i += blockDim.x) sh[i] = slots_g[i];
+        for (uint64_t i = threadIdx.x; i <= nheads; i += blockDim.x) sh[nslots + i] = heads_g[i];
+        __syncthreads();
+        slots = sh; heads = sh + nslots;
+    }
+    const uint64_t mask = nslots - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t s = hash_prefix(pimg, np, i, pbytes) & mask;
+        uint32_t l = 0, c = 0;
+        for (;;) {
+            uint32_t j = slots[s];
+            if (j == EMPTY) break;
+            uint32_t r = heads[j];
+            if (prefix_equal2(pimg, np, i, iimg, ni, r, pbytes)) { l = r; c = heads[j + 1] - r; break; }
+            s = (s + 1) & mask;
+        }
+        lo[i] = l; cnt[i] = c;
+    }
+}
+
+__global__ void expand_pairs_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ pos,
+                                    uint32_t* pid, uint32_t* iid, uint64_t np) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    uint32_t c = cnt[i], p = pos[i], l = lo[i];
+    for (uint32_t j = 0; j < c; j++) { pid[p + j] = (uint32_t)i; iid[p + j] = l + j; }
+}
+__global__ void zero_flag_kernel(const uint32_t* __restrict__ cnt, uint32_t* flag, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = cnt[i] == 0 ? 1u : 0u;
+}
+__global__ void compact_ids2_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, uint32_t* ids, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) ids[pos[i]] = (uint32_t)i;
+}
+
+static uint64_t read_u64(Ctx* c, const void* dev) {
+    uint64_t* h = (uint64_t*)c->pinned_scratch(8);
+    CPB_CUDA(cudaMemcpyAsync(h, dev, 8, cudaMemcpyDeviceToHost, c->stream));
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    return *h;
+}
+
+static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
+    auto it = ix.hash.find(nk);
+    if (it != ix.hash.end()) return it->second;
+    HashTable ht;
+    ht.nkeys = nk; ht.pbytes = prefix_bytes(ix, nk);
+    const uint64_t n = (uint64_t)ix.table->nrows;
+    Buf head = dev_alloc(c, (n + 1) * 4), pos = dev_alloc(c, (n + 1) * 4), tot = dev_alloc(c, 8);
+    {
+        KernelTimer kt(c, "hash_heads", (uint64_t)ix.image_words * n * 8 + n * 4);
+        head_flags2_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, head->as<uint32_t>());
+        CPB_CUDA(cudaGetLastError());
+    }
+    exclusive_scan_u32(c, head->as<uint32_t>(), pos->as<uint32_t>(), n, tot->as<uint64_t>());
+    ht.nheads = read_u64(c, tot->p);
+    ht.heads = dev_alloc(c, (ht.nheads + 1) * 4);
+    compact_heads_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(head->as<uint32_t>(), pos->as<uint32_t>(), ht.heads->as<uint32_t>(), n);
+    uint64_t want = std::max<uint64_t>(16, ht.nheads * 2);
+    ht.nslots = 1; while (ht.nslots < want) ht.nslots <<= 1;
+    ht.slots = dev_alloc(c, ht.nslots * 4);
+    CPB_CUDA(cudaMemsetAsync(ht.slots->p, 0xff, ht.nslots * 4, c->stream));
+    {
+        KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8));
+        hash_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
+                                                                        ht.slots->as<uint32_t>(), ht.nslots - 1);
+        CPB_CUDA(cudaGetLastError());
+    }
+    return ix.hash.emplace(nk, std::move(ht)).first->second;
+}
+
+std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const std::vector<std::string>& cols, bool anti,
+                                   DataError* derr, bool* failed) {
+    *failed = false;
+    const uint64_t np = (uint64_t)probe.nrows, ni = (uint64_t)ix.table->nrows;
+    const int nk = (int)cols.size();
+    std::vector<int> pidx;
+    for (int k = 0; k < nk; k++) {
+        int ci = probe.find(cols[k]);
+        if (ci < 0 && np > 0) {  // row.SelectValues(columns...) fails on the first probe row (csvplus.go:556, :145)
+            *failed = true;
+            *derr = DataError{CPB_E_MISSING_COLUMN, k, probe.first_line, true, "missing column " + go_quote(cols[k])};
+            return nullptr;
+        }
+        pidx.push_back(ci);
+    }
+    // output schema: mergeRows(indexRow, probeRow) — probe wins name collisions (csvplus.go:571-583)
+    std::vector<const Column*> icols, pcols;
+    if (!anti) for (auto& col : ix.table->cols) if (probe.find(col.name) < 0) icols.push_back(&col);
+    for (auto& col : probe.cols) pcols.push_back(&col);
+
+    auto out = std::make_shared<Table>(); out->ctx = c; out->first_line = probe.first_line;
+    auto empty_result = [&]() {
+        Table e; e.ctx = c; e.nrows = 0;
+        for (auto* p : icols) e.cols.push_back(*p);
+        for (auto* p : pcols) e.cols.push_back(*p);
+        return gather_rows(c, e, nullptr, 0);
+    };
+    if (np == 0) return empty_result();
+    Buf lo = dev_alloc(c, np * 4), cnt = dev_alloc(c, (np + 1) * 4);
+    if (ni == 0) {
+        CPB_CUDA(cudaMemsetAsync(cnt->p, 0, (np + 1) * 4, c->stream));
+    } else {
+        HashTable& ht = ensure_hash(c, ix, nk);
+        std::vector<uint32_t> widths(ix.key_width.begin(), ix.key_width.begin() + nk);
+        uint32_t pwords = 0;
+        Buf pimg = pack_with_widths(c, probe, pidx, widths, &pwords);
+        // algorithmic bytes: probe keys once + build table once
+        uint64_t algo = np * ((uint64_t)pwords * 8 + 8) + ht.nslots * 4 + ht.nheads * ((uint64_t)ht.pbytes + 4);
+        size_t smem = (ht.nslots + ht.nheads + 1) * 4;
+        KernelTimer kt(c, "join_probe", algo);
+        if (smem <= 200 * 1024) {
+            static bool configured = false;
+            if (!configured) { CPB_CUDA(cudaFuncSetAttribute(join_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+            uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count);
+            join_probe_kernel<true><<<grid, 256, smem, c->stream>>>(pimg->as<uint64_t>(), np, ix.image->as<uint64_t>(), ni, ht.pbytes,
+                                                                    ht.slots->as<uint32_t>(), ht.nslots, ht.heads->as<uint32_t>(), ht.nheads,
+                                                                    lo->as<uint32_t>(), cnt->as<uint32_t>());
+        } else {
+            uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
+            join_probe_kernel<false><<<grid, 256, 0, c->stream>>>(pimg->as<uint64_t>(), np, ix.image->as<uint64_t>(), ni, ht.pbytes,
+                                                                  ht.slots->as<uint32_t>(), ht.nslots, ht.heads->as<uint32_t>(), ht.nheads,
+                                                                  lo->as<uint32_t>(), cnt->as<uint32_t>());
+        }
+        CPB_CUDA(cudaGetLastError());
+    }
+    Buf tot = dev_alloc(c, 8);
+    if (anti) {
+        Buf flag = dev_alloc(c, np * 4), pos = dev_alloc(c, (np + 1) * 4);
+        zero_flag_kernel<<<nblk(np, 256), 256, 0, c->stream>>>(cnt->as<uint32_t>(), flag->as<uint32_t>(), np);
+        exclusive_scan_u32(c, flag->as<uint32_t>(), pos->as<uint32_t>(), np, tot->as<uint64_t>());
+        uint64_t m = read_u64(c, tot->p);
+        Buf ids = dev_alloc(c, (m + 1) * 4);
+        compact_ids2_kernel<<<nblk(np, 256), 256, 0, c->stream>>>(flag->as<uint32_t>(), pos->as<uint32_t>(), ids->as<uint32_t>(), np);
+        CPB_CUDA(cudaGetLastError());
+        auto r = gather_rows(c, probe, ids->as<uint32_t>(), (int64_t)m);
+        r->first_line = probe.first_line;
+        return r;
+    }
+    Buf pos = dev_alloc(c, (np + 1) * 4);
+    exclusive_scan_u32(c, cnt->as<uint32_t>(), pos->as<uint32_t>(), np, tot->as<uint64_t>());
+    const uint64_t m = read_u64(c, tot->p);
+    if (m > 0xfffffffeull) throw DataError{CPB_E_TOO_LARGE, -1, 0, false, "join result exceeds 2^32-2 rows; probe in smaller batches"};
+    if (m == 0) return empty_result();
+    Buf pid = dev_alloc(c, m * 4), iid = dev_alloc(c, m * 4);
+    {
+        KernelTimer kt(c, "join_pairs", np * 12 + m * 8);
+        expand_pairs_kernel<<<nblk(np, 256), 256, 0, c->stream>>>(lo->as<uint32_t>(), cnt->as<uint32_t>(), pos->as<uint32_t>(), pid->as<uint32_t>(),
+                                                                  iid->as<uint32_t>(), np);
+        CPB_CUDA(cudaGetLastError());
+    }
+    Table it; it.ctx = c; it.nrows = (int64_t)ni;
+    for (auto* p : icols) it.cols.push_back(*p);
+    Table pt; pt.ctx = c; pt.nrows = (int64_t)np;
+    for (auto* p : pcols) pt.cols.push_back(*p);
+    auto gi = gather_rows(c, it, iid->as<uint32_t>(), (int64_t)m);
+    auto gp = gather_rows(c, pt, pid->as<uint32_t>(), (int64_t)m);
+    out->nrows = (int64_t)m;
+    for (auto& col : gi->cols) out->cols.push_back(col);
+    for (auto& col : gp->cols) out->cols.push_back(col);
+    return out;
+}
+
+// ------------------------------------------------------------------ Index.Find: [lower, upper) of a key prefix
+__global__ void find_range_kernel(const uint64_t* __restrict__ image, uint64_t n, const uint64_t* __restrict__ val, uint32_t pbytes,
+                                  unsigned long long* out) {
+    // compare row r's first pbytes with val: <0, 0, >0
+    auto cmp = [&](uint64_t r) {
+        uint32_t full = pbytes >> 3, rem = pbytes & 7;
+        for (uint32_t w = 0; w < full; w++) {
+            uint64_t a = image[(uint64_t)w * n + r], b = val[w];
+            if (a != b) return a < b ? -1 : 1;
+        }
+        if (rem) {
+            uint64_t m = ~0ull << (8 * (8 - rem));
+            uint64_t a = image[(uint64_t)full * n + r] & m, b = val[full] & m;
+            if (a != b) return a < b ? -1 : 1;
+        }
+        return 0;
+    };
+    uint64_t i = 0, j = n;  // lower bound: first row >= val
+    while (i < j) { uint64_t h = i + (j - i) / 2; if (cmp(h) < 0) i = h + 1; else j = h; }
+    out[0] = i;
+    j = n;                  // upper bound: first row > val
+    while (i < j) { uint64_t h = i + (j - i) / 2; if (cmp(h) <= 0) i = h + 1; else j = h; }
+    out[1] = i;
+}
+
+void find_range(Ctx* c, Index& ix, const std::vector<std::string>& values, int64_t* lo, int64_t* hi) {
+    const uint64_t n = (uint64_t)ix.table->nrows;
+    *lo = 0; *hi = 0;
+    if (n == 0) return;
+    // pack the lookup values on the host with the index's widths (a handful of bytes)
+    std::vector<uint8_t> img((size_t)ix.image_words * 8 + 8, 0);
+    size_t b = 0;
+    for (size_t k = 0; k < values.size(); k++) {
+        uint32_t w = ix.key_width[k], lb = w < 255 ? 1 : (w < 65535 ? 2 : 4);
+        for (uint32_t i = 0; i < w; i++) img[b++] = i < values[k].size() ? (uint8_t)values[k][i] : 0;
+        uint32_t lf = values[k].size() > w ? 0xffffffffu : (uint32_t)values[k].size();
+        for (int i = (int)lb - 1; i >= 0; i--) img[b++] = (lf >> (8 * i)) & 0xff;
+    }
+    std::vector<uint64_t> words(ix.image_words + 1, 0);
+    for (size_t w = 0; w < words.size() && w * 8 < img.size(); w++)
+        for (int i = 0; i < 8 && w * 8 + i < img.size(); i++) words[w] |= (uint64_t)img[w * 8 + i] << (8 * (7 - i));
+    Buf dv = dev_alloc(c, words.size() * 8), out = dev_alloc(c, 16);
+    CPB_CUDA(cudaMemcpyAsync(dv->p, words.data(), words.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    {
+        KernelTimer kt(c, "index_find", 0);
+        find_range_kernel<<<1, 1, 0, c->stream>>>(ix.image->as<uint64_t>(), n, dv->as<uint64_t>(), (uint32_t)b, (unsigned long long*)out->p);
+        CPB_CUDA(cudaGetLastError());
+    }
+    uint64_t* h = (uint64_t*)c->pinned_scratch(16);
+    CPB_CUDA(cudaMemcpyAsync(h, out->p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    *lo = (int64_t)h[0]; *hi = (int64_t)h[1];
+}
+
+}  // namespace cpb

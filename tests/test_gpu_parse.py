@@ -1,0 +1,192 @@
+"""GPU parity of the fused parse (+select +filter) path against the CPU oracle, through the C ABI.
+
+Mirrors the reference's TestSimpleDataSource / TestErrors (csvplus_test.go:118-151, :808-909) and adds
+the encoding/csv edge cases the reference itself never exercises: quotes, "" escapes, CRLF,
+blank lines, ragged rows, records crossing tile and window boundaries, error ordinals."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.helpers import assert_table_equals_oracle, check_parity, gpu_ctx, people_csv, random_csv, run_both
+from tests.test_oracle_kat import KATS
+
+pytestmark = pytest.mark.gpu
+
+
+def _default_opts(o):
+    return not (o.comment or o.lazy_quotes or o.trim_leading_space or ord(o.comma) >= 0x80)
+
+
+@pytest.mark.parametrize("i", [i for i, k in enumerate(KATS) if _default_opts(k[1])])
+def test_kat_vectors_through_reader(i):
+    """every default-option vector of SURVEY App. A.3, first as Reader(header from row 1), then headerless"""
+    data, opts, _, _ = KATS[i]
+    check_parity(data, opts=opts)
+    o2 = orc.Opts(comma=opts.comma, fields_per_record=-1)
+    check_parity(data, opts=o2, assume={"a": 0, "b": 1, "c": 2, "d": 3})
+    o3 = orc.Opts(comma=opts.comma, fields_per_record=opts.fields_per_record)
+    check_parity(data, opts=o3, assume={"a": 0})
+
+
+def test_simple_data_source():
+    # csvplus_test.go:118-151: SelectColumns + Filter(Any(Like, Like))
+    import csvplus_b200 as cp
+    data = people_csv(120)
+    hdr = sorted(["id", "name", "surname", "born"])
+    src = cp.Take(cp.FromBytes(data).SelectColumns(*hdr)).Filter(cp.Any(cp.Like({"name": "Jack"}), cp.Like({"name": "Amelia"})))
+    n = 0
+    for row in src.ToRows():
+        assert row["name"] in ("Jack", "Amelia")
+        assert len(row) == 4 and sorted(row) == hdr
+        n += 1
+    assert n == 12 * 2
+
+
+def test_reader_errors():
+    # csvplus_test.go:810-815, :886-908 + App. A ordinals
+    import csvplus_b200 as cp
+    data = people_csv(120)
+    with pytest.raises(cp.DataSourceError) as e:
+        cp.Take(cp.FromBytes(data).SelectColumns("id", "name", "xxx")).ToRows()
+    assert str(e.value).endswith("row 1: column not found: xxx")
+    with pytest.raises(ValueError):  # duplicate column name panics, :818-823
+        cp.FromBytes(data).SelectColumns("id", "name", "id")
+    with pytest.raises(cp.DataSourceError) as e:
+        cp.Take(cp.FromBytes(data).ExpectHeader({"name": 1, "surname": 3})).ToRows()
+    assert str(e.value).endswith('row 1: misplaced column "surname": expected at pos. 3, but found at pos. 2')
+    with pytest.raises(cp.DataSourceError) as e:
+        cp.Take(cp.FromBytes(data).ExpectHeader({"name": 1, "surname": 25})).ToRows()
+    assert str(e.value).endswith('row 1: misplaced column "surname": expected at pos. 25, but found at pos. 2')
+    for bad in [b"a,b\n1,2\n3\n4,5\n", b'a,b\n1,2\n\n3,"x"y\n', b"", b'a,b\n1,2\n3,4"\n5,6\n', b'a,b\n"1,2\n3,4\n',
+                b"a,b\n1,2,3\n", b"a\n\n\n\r\n"]:
+        check_parity(bad)
+    check_parity(b"a,b\n1,2\n3\n", opts=orc.Opts(fields_per_record=-1), select=["b"])
+    check_parity(b"1,2\n3,4\n", assume={"x": 0, "y": 5})
+    check_parity(b"1,2\n3,4\n", assume={"x": 0, "y": 1})
+    check_parity(b"a,b\n1,2\n", opts=orc.Opts(fields_per_record=3))
+    check_parity(b"a,b,c\n1,2\n", opts=orc.Opts(fields_per_record=3))
+    check_parity(b"a,b\n1,2\n", opts=orc.Opts(comma="\n"))  # invalid delimiter
+
+
+def test_rows_before_error_are_delivered():
+    data = b"k,v\n" + b"".join(b"%d,x%d\n" % (i, i) for i in range(5000)) + b'5000,"bad"x\n' + b"5001,y\n" * 2000
+    t, gerr, orows = run_both(data)
+    assert str(gerr) == orows.error == 'row 5002: extraneous or missing " in quoted-field'
+    assert_table_equals_oracle(t, orows)
+    assert len(t) == 5000
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_adversarial_small(seed):
+    data = random_csv(seed, nrows=400, ncols=4 + seed % 3, quoted_p=0.4, crlf_p=0.4, blank_p=0.2,
+                      trailing_newline=seed % 2 == 0)
+    check_parity(data)
+    check_parity(data, select=["c2", "c0"])
+    check_parity(data, select=["c1"], like={"c1": ""})
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_adversarial_multi_tile(seed):
+    """several 32 KiB tiles, records crossing tile/window edges, quoted newlines spanning tiles"""
+    data = random_csv(100 + seed, nrows=6000, ncols=5, quoted_p=0.35, long_p=0.004, crlf_p=0.3, blank_p=0.05)
+    assert len(data) > 200_000
+    check_parity(data)
+    check_parity(data, select=["c4", "c1"])
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_ragged(seed):
+    data = random_csv(200 + seed, nrows=3000, ncols=5, quoted_p=0.2, ragged_p=0.3)
+    check_parity(data, opts=orc.Opts(fields_per_record=-1))
+    check_parity(data, opts=orc.Opts(fields_per_record=-1), select=["c3", "c0"])
+    check_parity(data)  # auto field count: first ragged row is the error
+
+
+def test_error_inside_big_input_picks_first():
+    good = random_csv(7, nrows=20000, ncols=4, quoted_p=0.3)
+    bad1 = good + b'x,y"z,1,2\n' + random_csv(8, nrows=20000, ncols=4, quoted_p=0.3, header=False) + b'"open,1,2,3\n'
+    check_parity(bad1)
+
+
+def test_quote_parity_across_many_tiles():
+    """a quoted field longer than several tiles: chain-1 parity carry and the slow path past the window"""
+    big = b"A" * 150_000 + b'""' + b"\n" * 10 + b"B" * 50_000
+    data = b'k,v\n1,"' + big + b'"\n2,plain\n3,"x\r\ny"\n' + b"".join(b"%d,z\n" % i for i in range(4, 3000))
+    t, _ = check_parity(data)
+    assert len(t) == 2999
+
+
+def test_delimiter_and_filters():
+    data = b"a;b;c\n1;x;y\n2;x;z\n3;w;y\n"
+    check_parity(data, opts=orc.Opts(comma=";"), like={"b": "x"})
+    check_parity(data, opts=orc.Opts(comma=";"), select=["c", "a"], like={"c": "y", "a": "3"})
+    check_parity(data, opts=orc.Opts(comma=";"), select=["c", "a"], like={"zzz": "y"})  # missing column => false
+    check_parity(data.replace(b";", b"\t"), opts=orc.Opts(comma="\t"))
+
+
+def test_predicate_combinators():
+    import csvplus_b200 as cp
+    data = people_csv(120)
+    o = orc.reader_rows(data)
+    cases = [
+        (cp.Any(cp.Like({"name": "Jack"}), cp.Like({"surname": "Smith"})), orc.Any(orc.Like({"name": "Jack"}), orc.Like({"surname": "Smith"}))),
+        (cp.All(cp.Like({"name": "Jack"}), cp.Not(cp.Like({"surname": "Smith"}))), orc.All(orc.Like({"name": "Jack"}), orc.Not(orc.Like({"surname": "Smith"})))),
+        (cp.Not(cp.Any(cp.Like({"name": "Jack"}), cp.Like({"name": "Ava", "surname": "Jones"}))),
+         orc.Not(orc.Any(orc.Like({"name": "Jack"}), orc.Like({"name": "Ava", "surname": "Jones"})))),
+        (cp.All(), orc.All()), (cp.Any(), orc.Any()),
+    ]
+    for gp, op in cases:
+        t, err = cp.parse_csv(gpu_ctx(), data, pred=gp)
+        assert err is None
+        assert_table_equals_oracle(t, o.filter(op))
+        # the same predicate on a materialised table (cpb_table_filter)
+        t0, _ = cp.parse_csv(gpu_ctx(), data)
+        assert_table_equals_oracle(t0.filter(gp), o.filter(op))
+
+
+def test_synthetic_people_config1():
+    """BASELINE config 1 shape at 200 k rows: Take(FromFile).Filter(Like{name: Amelia}).ToRows, all 6 columns"""
+    import csvplus_b200 as cp
+    ctx = gpu_ctx()
+    buf = ctx.gen_csv("people", (0, 200_000))
+    host = buf.to_host()
+    t, err = cp.parse_csv(ctx, buf, pred=cp.Like({"name": "Amelia"}))
+    assert err is None
+    o = orc.reader_rows(host, pred=orc.Like({"name": "Amelia"}))
+    assert 15_000 < len(o) < 25_000
+    assert_table_equals_oracle(t, o)
+    # config 2 shape: SelectColumns(name, surname, id) + Filter
+    t, err = cp.parse_csv(ctx, buf, spec=[("name", -1), ("surname", -1), ("id", -1)], pred=cp.Like({"name": "Amelia"}))
+    o = orc.reader_rows(host, select=["name", "surname", "id"], pred=orc.Like({"name": "Amelia"}))
+    assert_table_equals_oracle(t, o)
+    # host-memory entry (H2D inside the call) gives the same table
+    t2, _ = cp.parse_csv(ctx, host, spec=[("name", -1), ("surname", -1), ("id", -1)], pred=cp.Like({"name": "Amelia"}))
+    assert_table_equals_oracle(t2, o)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 at 20 M rows (≈0.9 GB): size-independent properties instead of the oracle:
+    row count conservation across a partition of predicates, and per-column byte checksums."""
+    import csvplus_b200 as cp
+    ctx = gpu_ctx()
+    n = 20_000_000
+    buf = ctx.gen_csv("people", (0, n))
+    names = ["Amelia", "Olivia", "Emily", "Ava", "Isla", "Oliver", "Jack", "Harry", "Jacob", "Charlie"]
+    total = 0
+    for nm in names:
+        t, err = cp.parse_csv(ctx, buf, spec=[("name", -1), ("id", -1)], pred=cp.Like({"name": nm}))
+        assert err is None
+        total += len(t)
+        off, data = t.column("name", 0, min(len(t), 1000))
+        assert data.tobytes() == nm.encode() * min(len(t), 1000)
+    assert total == n
+    t, err = cp.parse_csv(ctx, buf, spec=[("id", -1)])
+    assert err is None and len(t) == n
+    # ids are the row ordinals: total digits = sum of decimal lengths of 0..n-1
+    nb = sum((min(n, 10 ** (d + 1)) - 10 ** d) * (d + 1) for d in range(8) if 10 ** d < n) + 1
+    off, data = t.column("id", n - 3, n)
+    assert data.tobytes() == b"%d%d%d" % (n - 3, n - 2, n - 1)
+    import ctypes as C
+    nbytes = C.c_uint64()
+    ctx.lib.cpb_table_col_bytes(ctx.h, t.h, 0, 0, n, C.byref(nbytes))
+    assert nbytes.value == nb
