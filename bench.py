@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract of the csvplus_b200 hot path.
+
+Headline workload (BASELINE.json configs[2], the "rows/sec end-to-end Join" half of the metric):
+    customers (10 M rows, 6 cols)  -> parse + SelectColumns(id,name,surname) -> UniqueIndexOn(id)
+    orders    (100 M rows per GPU) -> parse + SelectColumns(cust_id,prod_id,qty,ts) -> Join(idx, "cust_id")
+one "step" = one full pass of that pipeline over synthetic CSV (SURVEY §8d shapes).
+  value = probe rows/s with the CSV bytes already resident in HBM (whole job, all ranks);
+  e2e   = the same through the public API with HOST (pinned) CSV buffers: H2D inside the timed region and
+          a D2H read of the result summary (row count + bytes per column).
+The "CSV parse GB/s" half of the metric (BASELINE.json configs[1]: people 100 M rows x 6 cols, parse +
+SelectColumns(name,surname,id) + Filter(Like{name: Amelia})) is timed in the same run and reported under
+"csv_parse", together with its own roofline.  "roofline" describes the dominant kernel of the step (csv_scan).
+
+Multi-GPU (torchrun, one rank per GPU): the probe stream is sharded by row range (100 M orders per rank, weak
+scaling); each rank parses 1/N of the build side and the build-side columns are all-gathered with NCCL.
+
+--impl reference: the reference (pure Go) cannot be built here (no Go toolchain), so the arm times the CPU
+oracle port of the same pipeline (oracle/, kind "port") on a bounded sample, single-threaded because the
+reference is strictly single-threaded (csvplus.go has no goroutines).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0xC5B200
+CUST_COLS = [("id", -1), ("name", -1), ("surname", -1)]
+ORDER_COLS = [("cust_id", -1), ("prod_id", -1), ("qty", -1), ("ts", -1)]
+PEOPLE_COLS = [("name", -1), ("surname", -1), ("id", -1)]
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    def __init__(self, index: int):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline (oracle port)
+def cpu_join_sample(n_orders: int, n_cust: int, ctx=None, data=None):
+    """the same pipeline in the CPU oracle, single thread; returns (rows/s, seconds, sample text)"""
+    from oracle import oracle as orc
+    if data is None:
+        cust = ctx.gen_csv("customers", (0, n_cust), seed=SEED, n_cust=n_cust, permute=True).to_host()
+        orders = ctx.gen_csv("orders", (0, n_orders), seed=SEED, n_cust=n_cust, n_prod=1_000_000).to_host()
+    else:
+        cust, orders = data
+    t0 = time.perf_counter()
+    idx = orc.reader_rows(cust, select=[c for c, _ in CUST_COLS]).unique_index_on("id", stable=False)
+    joined = orc.reader_rows(orders, select=[c for c, _ in ORDER_COLS]).join(idx, "cust_id")
+    n = len(joined)
+    dt = time.perf_counter() - t0
+    assert n == n_orders
+    return n_orders / dt, dt, f"orders {n_orders} rows x customers {n_cust} rows, same generator, 1 thread"
+
+
+def cpu_parse_sample(n_rows: int, ctx):
+    from oracle import oracle as orc
+    people = ctx.gen_csv("people", (0, n_rows), seed=SEED).to_host()
+    t0 = time.perf_counter()
+    r = orc.reader_rows(people, select=[c for c, _ in PEOPLE_COLS], pred=orc.Like({"name": "Amelia"}))
+    n = len(r)
+    dt = time.perf_counter() - t0
+    return people.size / dt / 1e9, n_rows / dt, dt, n
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import csvplus_b200 as cp
+    ctx = cp.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    n_orders, n_cust = args.ref_orders, args.ref_customers
+    cust = ctx.gen_csv("customers", (0, n_cust), seed=SEED, n_cust=n_cust, permute=True).to_host()
+    orders = ctx.gen_csv("orders", (0, n_orders), seed=SEED, n_cust=n_cust, n_prod=1_000_000).to_host()
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, dt, sample = cpu_join_sample(n_orders, n_cust, data=(cust, orders))
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = n_orders / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "rows/sec end-to-end Join", "value": value, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": 1, "kind": "port",
+                         "sample": sample + " (oracle/ C++ restatement of csvplus; the Go reference has no toolchain here)"},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {"workload": "orders(100 M rows/GPU) x customers(10 M): parse+SelectColumns, UniqueIndexOn(id), Join(cust_id) "
+                        "[BASELINE configs[2]; configs[1] parse+filter reported under csv_parse]",
+            "orders_rows_per_gpu": ORD_ROWS, "customers_rows": CUST_ROWS, "people_rows": PEOPLE_ROWS,
+            "parallelism": f"row-range shards x{world}, build side all-gathered (NCCL)" if world > 1 else "single GPU",
+            "l2": "inputs (>= 0.44 GB per pass) exceed the 126 MB L2; no flush needed"}
+
+
+ORD_ROWS = 100_000_000
+CUST_ROWS = 10_000_000
+PEOPLE_ROWS = 100_000_000
+
+
+def main():
+    global ORD_ROWS, CUST_ROWS, PEOPLE_ROWS
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--orders", type=int, default=ORD_ROWS, help="probe rows per GPU")
+    ap.add_argument("--customers", type=int, default=CUST_ROWS)
+    ap.add_argument("--people", type=int, default=PEOPLE_ROWS)
+    ap.add_argument("--ref-orders", type=int, default=2_000_000)
+    ap.add_argument("--ref-customers", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    ORD_ROWS, CUST_ROWS, PEOPLE_ROWS = args.orders, args.customers, args.people
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import csvplus_b200 as cp
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = cp.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    # ---------------- synthetic inputs (device resident; pinned host copies for the e2e leg)
+    n_prod = 1_000_000
+    cust_lo, cust_hi = rank * CUST_ROWS // world, (rank + 1) * CUST_ROWS // world
+    d_cust = ctx.gen_csv("customers", (cust_lo, cust_hi), seed=SEED, n_cust=CUST_ROWS, permute=True, header=True)
+    d_orders = ctx.gen_csv("orders", (rank * ORD_ROWS, (rank + 1) * ORD_ROWS), seed=SEED, n_cust=CUST_ROWS, n_prod=n_prod, header=True)
+    d_people = ctx.gen_csv("people", (rank * PEOPLE_ROWS, (rank + 1) * PEOPLE_ROWS), seed=SEED, header=True)
+    ctx.sync()
+
+    from csvplus_b200.dist import allgather_table
+
+    def join_step(cust_src, orders_src):
+        tc, err = cp.parse_csv(ctx, cust_src, spec=CUST_COLS)
+        assert err is None
+        if world > 1:
+            tc = allgather_table(ctx, tc, dist)
+        idx = tc.index_on("id", unique=True)
+        to, err = cp.parse_csv(ctx, orders_src, spec=ORDER_COLS)
+        assert err is None
+        j = to.join(idx, "cust_id")
+        return j
+
+    def parse_step(people_src):
+        t, err = cp.parse_csv(ctx, people_src, spec=PEOPLE_COLS, pred=cp.Like({"name": "Amelia"}))
+        assert err is None
+        return t
+
+    def timed(fn, steps, warmup, sampler_dev=None):
+        for _ in range(warmup):
+            r = fn(); del r
+        ctx.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(sampler_dev) if sampler_dev is not None else None
+        ctx.stats(enable=True, reset=True)
+        l0 = ctx.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rows = 0
+        for _ in range(steps):
+            r = fn(); rows = len(r); del r
+        e1.record(stream)
+        ctx.sync(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            dist.barrier()
+            tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        stats = ctx.stats()
+        ctx.stats(enable=False)
+        clocks = sampler.stop() if sampler else None
+        return ms / steps, rows, stats, ctx.kernel_launches() - l0, clocks
+
+    # ---------------- device-resident timing (value)
+    ms_join, out_rows, st_join, launches, clocks = timed(lambda: join_step(d_cust, d_orders), args.steps, args.warmup, local)
+    ms_parse, parse_rows, st_parse, _, _ = timed(lambda: parse_step(d_people), args.steps, args.warmup)
+    peak, peak_kind = hbm_peak()
+
+    def roof(st, traffic=None):
+        s = st.get("csv_scan")
+        if not s or not s["launches"]:
+            return None
+        per_launch_bytes = s["algo_bytes"] / s["launches"]
+        per_launch_ms = s["ms"] / s["launches"]
+        ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "csv_scan", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_kind": f"of {peak_kind}", "launches": s["launches"], "ms_per_launch": per_launch_ms,
+                "algo_bytes_per_launch": per_launch_bytes}
+
+    # ---------------- end-to-end timing from pinned host buffers
+    e2e = None
+    parse_e2e = None
+    if not args.no_e2e:
+        h_cust, h_orders, h_people = ctx.host_alloc(d_cust.nbytes), ctx.host_alloc(d_orders.nbytes), ctx.host_alloc(d_people.nbytes)
+        for h, d in ((h_cust, d_cust), (h_orders, d_orders), (h_people, d_people)):
+            ctx.lib.cpb_memcpy_d2h(ctx.h, h.ptr, d.ptr, d.nbytes)
+        summary_bytes = [0]
+
+        def join_e2e():
+            j = join_step(h_cust, h_orders)
+            # D2H read of the step's result: row count + byte total of every output column
+            import ctypes as C
+            nb = C.c_uint64(); tot = 0
+            for i in range(len(j.columns)):
+                ctx.lib.cpb_table_col_bytes(ctx.h, j.h, i, 0, len(j), C.byref(nb)); tot += nb.value
+            summary_bytes[0] = 8 * len(j.columns) + 8
+            return j
+
+        ms_e2e, _, _, _, _ = timed(join_e2e, args.steps, args.warmup)
+        e2e = {"value": world * ORD_ROWS / (ms_e2e * 1e-3), "unit": "rows/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": h_cust.nbytes + h_orders.nbytes, "d2h_bytes_per_step": summary_bytes[0],
+               "note": "pinned host CSV -> H2D -> parse/index/join on the GPU; result stays in HBM, its summary is read back"}
+        ms_pe2e, _, _, _, _ = timed(lambda: parse_step(h_people), args.steps, args.warmup)
+        parse_e2e = {"value": world * h_people.nbytes / (ms_pe2e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_pe2e,
+                     "h2d_bytes_per_step": h_people.nbytes}
+
+    # ---------------- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, sample = cpu_join_sample(args.ref_orders, args.ref_customers, ctx=ctx)
+        pg, pr, pdt, _ = cpu_parse_sample(4_000_000, ctx)
+        cpu = {"value": v, "unit": "rows/s", "cores": 1, "kind": "port", "seconds": dt,
+               "sample": sample + "; C++ restatement proxy of the Go reference (single-threaded like it), host cores: %d" % (os.cpu_count() or 0),
+               "csv_parse": {"value": pg, "unit": "GB/s", "rows_per_s": pr, "sample": "people 4 M rows, parse+select+filter, 1 thread"}}
+
+    if rank == 0:
+        line = {
+            "metric": "rows/sec end-to-end Join", "value": world * ORD_ROWS / (ms_join * 1e-3), "unit": "rows/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_join, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks, "gpu_launches": launches, "out_rows_per_gpu": out_rows,
+            "e2e": e2e,
+            "roofline": roof(st_join),
+            "csv_parse": {"metric": "CSV parse GB/s (configs[1]: parse+SelectColumns(name,surname,id)+Filter(Like name=Amelia))",
+                          "value": world * d_people.nbytes / (ms_parse * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_parse,
+                          "rows_per_s": world * PEOPLE_ROWS / (ms_parse * 1e-3), "rows_out_per_gpu": parse_rows,
+                          "input_bytes_per_gpu": d_people.nbytes, "roofline": roof(st_parse), "e2e": parse_e2e},
+            "cpu_baseline": cpu,
+            "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in sorted(st_join.items())},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,61 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: row-range sharding and the ragged all-gather
+that replicates the build-side columns."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from csvplus_b200.dist import allgather_ragged, shard_range
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(rank)
+        # a ragged "column": rank r holds r*7+3 values
+        lens = rng.integers(0, 9, size=rank * 7 + 3)
+        off = np.zeros(len(lens) + 1, np.uint32); off[1:] = np.cumsum(lens)
+        data = rng.integers(32, 127, size=int(off[-1]), dtype=np.uint8)
+        po = allgather_ragged(torch.from_numpy(off.view(np.uint8).copy()), dist)
+        pd = allgather_ragged(torch.from_numpy(data.copy()), dist)
+        empty = allgather_ragged(torch.zeros(0 if rank == 0 else 5, dtype=torch.uint8), dist)
+        q.put((rank, [p.numpy().tobytes() for p in po], [p.numpy().tobytes() for p in pd], [e.numel() for e in empty],
+               off.tobytes(), data.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_ragged_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    offs = [r[4] for r in res]; datas = [r[5] for r in res]
+    for rank, po, pd, empty, _, _ in res:
+        assert po == offs and pd == datas  # every rank sees every rank's columns, in rank order
+        assert empty == [0, 5]
+
+
+def test_shard_range_partitions_rows():
+    for total in (0, 1, 7, 100, 10_000_019):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
