@@ -97,16 +97,46 @@ __global__ void gather_len_kernel(const uint32_t* __restrict__ off, const uint32
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { uint32_t r = ids ? ids[i] : (uint32_t)i; out_len[i] = off[r + 1] - off[r]; }
 }
-// one thread per output value; ids==nullptr means identity (compaction of a view)
-__global__ void gather_copy_kernel(const uint32_t* __restrict__ src_off, const uint8_t* __restrict__ src, const uint32_t* __restrict__ ids,
-                                   const uint32_t* __restrict__ dst_off, uint8_t* __restrict__ dst, uint64_t n) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t r = ids ? ids[i] : (uint32_t)i;
-    uint32_t s = src_off[r], len = src_off[r + 1] - s, d = dst_off[i];
-    const uint8_t* sp = src + s;
-    uint8_t* dp = dst + d;
-    for (uint32_t k = 0; k < len; k++) dp[k] = sp[k];
+// One warp gathers 32 consecutive output values.  Their destination bytes are contiguous, so the lanes first
+// copy their (randomly placed) source strings into a per-warp shared-memory stage laid out like the
+// destination, then the warp writes the stage with aligned 16-byte stores: HBM/L2 see full sectors instead of one
+// scattered byte store per lane.  ids==nullptr means identity (compaction of a view).
+constexpr int GW_WARPS = 8;
+constexpr int GW_STAGE = 2048;  // bytes staged per warp; longer groups take the direct path
+__global__ void __launch_bounds__(GW_WARPS * 32) gather_copy_kernel(const uint32_t* __restrict__ src_off, const uint8_t* __restrict__ src,
+                                                                    const uint32_t* __restrict__ ids, const uint32_t* __restrict__ dst_off,
+                                                                    uint8_t* __restrict__ dst, uint64_t n) {
+    __shared__ __align__(16) uint8_t stage_all[GW_WARPS][GW_STAGE + 16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* stage = stage_all[warp];
+    const uint64_t nwarps = (uint64_t)gridDim.x * GW_WARPS;
+    for (uint64_t g = (uint64_t)blockIdx.x * GW_WARPS + warp; g * 32 < n; g += nwarps) {
+        const uint64_t i = g * 32 + lane;
+        uint32_t s = 0, len = 0, d = 0;
+        if (i < n) {
+            const uint32_t r = ids ? ids[i] : (uint32_t)i;
+            s = src_off[r]; len = src_off[r + 1] - s; d = dst_off[i];
+        }
+        const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+        const uint64_t last = (g * 32 + 31 < n ? g * 32 + 31 : n - 1) - g * 32;
+        const uint32_t dl = __shfl_sync(0xffffffffu, d + len, (int)last);
+        const uint32_t total = dl - d0, sh = d0 & 15u;
+        const uint8_t* sp = src + s;
+        if (sh + total <= GW_STAGE) {
+            uint8_t* q = stage + sh + (d - d0);
+            for (uint32_t k = 0; k < len; k++) q[k] = sp[k];
+            __syncwarp();
+            uint8_t* gb = dst + (d0 - sh);
+            for (uint32_t x = lane * 16; x < sh + total; x += 32 * 16) {
+                if (x >= sh && x + 16 <= sh + total) *reinterpret_cast<uint4*>(gb + x) = *reinterpret_cast<const uint4*>(stage + x);
+                else for (uint32_t y = x; y < x + 16; y++) if (y >= sh && y < sh + total) gb[y] = stage[y];
+            }
+            __syncwarp();
+        } else {
+            uint8_t* dp = dst + d;
+            for (uint32_t k = 0; k < len; k++) dp[k] = sp[k];
+        }
+    }
 }
 
 static inline uint32_t blocks_for(uint64_t n, int threads) { return (uint32_t)((n + threads - 1) / threads); }
@@ -138,7 +168,8 @@ static std::vector<Column> gather_columns(Ctx* c, const std::vector<const Column
         out[k].data = dev_alloc(c, tot[k] + 16);
         if (nout && tot[k]) {
             KernelTimer kt(c, "gather_copy", 2 * tot[k] + (uint64_t)nout * 12);
-            gather_copy_kernel<<<blocks_for(nout, 256), 256, 0, c->stream>>>(srcs[k]->off(), srcs[k]->bytes(), ids,
+            const uint32_t gblocks = (uint32_t)std::min<uint64_t>(((uint64_t)nout + GW_WARPS * 32 - 1) / (GW_WARPS * 32), (uint64_t)c->sm_count * 16);
+            gather_copy_kernel<<<gblocks, GW_WARPS * 32, 0, c->stream>>>(srcs[k]->off(), srcs[k]->bytes(), ids,
                                                                               out[k].offsets->as<uint32_t>(), out[k].data->as<uint8_t>(), (uint64_t)nout);
             CPB_CUDA(cudaGetLastError());
         }
