@@ -23,8 +23,18 @@ std::string go_quote(const std::string& s) {
     return r + "\"";
 }
 
+// Requests are rounded up to size classes (1/8 steps of the enclosing power of two, <= 12.5 % slack): batches of
+// slightly different sizes then ask the stream-ordered pool for identical blocks and reuse them instead of
+// mapping fresh physical memory (which costs tens of milliseconds per GB).
+static size_t size_class(size_t b) {
+    if (b < (1u << 20)) return (b + 511) & ~(size_t)511;
+    size_t p = 1;
+    while ((p << 1) <= b) p <<= 1;
+    const size_t step = p >> 3;
+    return (b + step - 1) / step * step;
+}
 DevBuf::DevBuf(Ctx* c, size_t bytes) : ctx(c), n(bytes) {
-    cudaError_t e = cudaMallocAsync(&p, bytes, c->pool, c->stream);
+    cudaError_t e = cudaMallocAsync(&p, size_class(bytes), c->pool, c->stream);
     if (e != cudaSuccess) { cudaGetLastError(); throw CudaFail{e, "cudaMallocAsync", __FILE__, __LINE__}; }
 }
 DevBuf::~DevBuf() {
@@ -130,7 +140,19 @@ int cpb_init(int device, cpb_ctx** out) {
         c->sm_count = prop.multiProcessorCount;
         c->smem_optin = prop.sharedMemPerBlockOptin;
         CPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        CPB_CUDA(cudaDeviceGetDefaultMemPool(&c->pool, device));
+        // a private stream-ordered pool per ctx: contexts running on different streams never wait on each other's
+        // frees (the shared default pool may insert cross-stream dependencies to recycle memory)
+        if (getenv("CPB_SHARED_POOL")) {
+            CPB_CUDA(cudaDeviceGetDefaultMemPool(&c->pool, device));
+        } else {
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
+            CPB_CUDA(cudaMemPoolCreate(&c->pool, &props));
+            c->own_pool = true;
+        }
         uint64_t thr = UINT64_MAX;  // keep freed blocks cached in the pool
         CPB_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
     } catch (...) {
@@ -150,6 +172,7 @@ void cpb_shutdown(cpb_ctx* h) {
     c->drain_events();
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaStreamDestroy(c->stream);
+    if (c->own_pool) cudaMemPoolDestroy(c->pool);
     delete h;
 }
 
@@ -229,7 +252,7 @@ int cpb_parse_csv(cpb_ctx* h, const void* bytes, uint64_t nbytes, int on_device,
     Buf staged;
     const uint8_t* dev = (const uint8_t*)bytes;
     if (!on_device) {
-        staged = dev_alloc(c, ((nbytes + 15) & ~15ull) + 16);
+        staged = dev_alloc(c, (nbytes + (32u << 20)) / (32u << 20) * (32u << 20));  // size class: batches reuse pool blocks
         if (nbytes) {
             KernelTimer kt(c, "h2d_input", nbytes, 0);
             CPB_CUDA(cudaMemcpyAsync(staged->p, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));

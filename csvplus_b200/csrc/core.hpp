@@ -107,6 +107,7 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaMemPool_t pool = nullptr;
+    bool own_pool = false;
     std::mutex mu;              // one call in flight per ctx
     std::string last_error;
     int sm_count = 148;

@@ -193,9 +193,23 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
     const uint64_t sample_bytes = h->sample_bytes, sample_newlines = h->sample_newlines;  // h aliases pinned scratch
     double avg = sample_newlines ? (double)sample_bytes / (double)sample_newlines : (double)n;
     if (avg < 2) avg = 2;
-    uint64_t row_cap = (uint64_t)((double)(n - data_start) / avg * 1.10) + 4096;
-    if (row_cap > (n - data_start) / 2 + 2) row_cap = (n - data_start) / 2 + 2;
-    std::vector<uint64_t> data_cap(nsel, std::min<uint64_t>(n - data_start, 0xffffffffull));
+    // Capacities are rounded up to size classes so that successive batches of slightly different sizes request
+    // identical blocks and are served from the stream-ordered pool instead of mapping fresh memory.
+    auto size_class = [](uint64_t v, uint64_t gran) { return (v + gran - 1) / gran * gran; };
+    const uint64_t body = n - data_start;
+    uint64_t row_cap = (uint64_t)((double)body / avg * 1.10) + 4096;
+    if (row_cap > body / 2 + 2) row_cap = body / 2 + 2;
+    row_cap = size_class(row_cap, 1u << 20);
+    // per-column bytes from the sampled mean field lengths (naive split of ~768 sampled lines); the worst case
+    // (all of the input) when a field was not sampled.  An underestimate costs one exact rerun, never correctness.
+    std::vector<uint64_t> data_cap(nsel, std::min<uint64_t>(body, 0xffffffffull));
+    const uint64_t samp_lines = h->samp_lines;
+    for (int k = 0; k < nsel && samp_lines >= 16; k++) {
+        if (fields[k] >= HDR_SAMPLE_FIELDS) continue;
+        double mean = (double)h->samp_field_bytes[fields[k]] / (double)samp_lines;
+        uint64_t est = (uint64_t)((double)row_cap * mean * 1.25) + (4u << 20);
+        data_cap[k] = std::min<uint64_t>(data_cap[k], size_class(est, 32u << 20));
+    }
 
     Buf state = dev_alloc(c, (size_t)P.ntiles * (8 + 16ull * NP) + 64 + sizeof(ParseResult));
     std::vector<Buf> offs(nsel), datas(nsel);

@@ -36,6 +36,7 @@ constexpr int LITS_SMEM = 256;
 constexpr int MAXSEL = CPB_MAX_PARSE_COLS;
 constexpr int HDR_MAX_FIELDS = 1024;
 constexpr int HDR_MAX_BYTES = 16384;
+constexpr int HDR_SAMPLE_FIELDS = 64;
 
 enum { K_OK = 0, K_BARE = CPB_E_BARE_QUOTE, K_QUOTE = CPB_E_QUOTE, K_FIELDS = CPB_E_FIELD_COUNT, K_COLIDX = CPB_E_COLUMN_INDEX };
 
@@ -150,6 +151,8 @@ struct HeaderOut {
     int32_t truncated;  // names did not fit
     uint64_t rec_start, data_start;
     uint64_t sample_bytes, sample_newlines;
+    unsigned long long samp_lines;                            // lines split naively for the capacity estimate
+    unsigned long long samp_field_bytes[HDR_SAMPLE_FIELDS];   // their bytes per field index
     uint32_t field_len[HDR_MAX_FIELDS];
     uint8_t bytes[HDR_MAX_BYTES];
 };
@@ -203,8 +206,34 @@ __global__ void csv_header_kernel(const uint8_t* in, uint64_t n, int delim, Head
         tot += hi - lo;
     }
     atomicAdd(&s_nl, cnt);
+    // mean field lengths: every thread splits one line (naively: quotes ignored — this only sizes buffers) in each window
+    __shared__ unsigned long long s_lines, s_fb[HDR_SAMPLE_FIELDS];
+    if (threadIdx.x == 0) s_lines = 0;
+    if (threadIdx.x < HDR_SAMPLE_FIELDS) s_fb[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) { out->sample_bytes = tot; out->sample_newlines = s_nl; }
+    for (int w = 0; w < 3; w++) {
+        uint64_t lo = w == 0 ? 0 : (w == 1 ? (n / 2) : (n > S ? n - S : 0));
+        uint64_t p = lo + (uint64_t)threadIdx.x * (S / blockDim.x);
+        uint64_t lim = p + 4096 < n ? p + 4096 : n;
+        while (p < lim && in[p] != '\n') p++;
+        p++;  // first byte of the next line
+        if (p >= n || p >= lim) continue;
+        lim = p + 4096 < n ? p + 4096 : n;
+        int f = 0; uint32_t len = 0; bool done = false;
+        for (; p < lim; p++) {
+            uint8_t ch = in[p];
+            if (ch == delim || ch == '\n') {
+                if (f < HDR_SAMPLE_FIELDS) atomicAdd(&s_fb[f], (unsigned long long)len);
+                f++; len = 0;
+                if (ch == '\n') { done = true; break; }
+            } else len++;
+        }
+        if (done) atomicAdd(&s_lines, 1ull);
+        else for (int g = 0; g < f && g < HDR_SAMPLE_FIELDS; g++) {}  // partial line: its complete fields stay counted (slight overestimate)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { out->sample_bytes = tot; out->sample_newlines = s_nl; out->samp_lines = s_lines; }
+    if (threadIdx.x < HDR_SAMPLE_FIELDS) out->samp_field_bytes[threadIdx.x] = s_fb[threadIdx.x];
 }
 
 // ------------------------------------------------------------------ main kernel
