@@ -35,20 +35,20 @@ const char* kind_text(int k) {
     }
 }
 
-template <int KMAX>
+template <int KMAX, bool EXACT>
 void launch_scan(Ctx* c, const ParseParams& P, uint64_t algo_bytes) {
     static bool configured = false;
     const size_t smem = sizeof(ParseSmem);
     if (!configured) {
-        CPB_CUDA(cudaFuncSetAttribute(csv_scan_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CPB_CUDA(cudaFuncSetAttribute(csv_scan_kernel<KMAX, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int occ = 0;
-    CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, csv_scan_kernel<KMAX>, THREADS, smem));
+    CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, csv_scan_kernel<KMAX, EXACT>, THREADS, smem));
     if (occ < 1) occ = 1;
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count * occ, P.ntiles);
     KernelTimer kt(c, "csv_scan", algo_bytes);
-    csv_scan_kernel<KMAX><<<grid, THREADS, smem, c->stream>>>(P);
+    csv_scan_kernel<KMAX, EXACT><<<grid, THREADS, smem, c->stream>>>(P);
     CPB_CUDA(cudaGetLastError());
 }
 
@@ -231,9 +231,17 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
         CPB_CUDA(cudaMemsetAsync(&P.result->err_key, 0xff, 24, c->stream));
         CPB_CUDA(cudaMemsetAsync(P.words, 0, (size_t)P.ntiles * (NP * 8 + 4), c->stream));
         uint64_t algo = n;  // S_in; S_out added by the caller of stats from the totals
-        if (nsel <= 4) launch_scan<4>(c, P, algo);
-        else if (nsel <= 8) launch_scan<8>(c, P, algo);
-        else launch_scan<16>(c, P, algo);
+        switch (nsel) {  // kernels specialised on the exact number of extracted columns (no per-column guards)
+            case 1: launch_scan<1, true>(c, P, algo); break;
+            case 2: launch_scan<2, true>(c, P, algo); break;
+            case 3: launch_scan<3, true>(c, P, algo); break;
+            case 4: launch_scan<4, true>(c, P, algo); break;
+            case 5: launch_scan<5, true>(c, P, algo); break;
+            case 6: launch_scan<6, true>(c, P, algo); break;
+            case 7: launch_scan<7, true>(c, P, algo); break;
+            case 8: launch_scan<8, true>(c, P, algo); break;
+            default: launch_scan<16, false>(c, P, algo); break;
+        }
         ParseResult* hr = (ParseResult*)c->pinned_scratch(sizeof(ParseResult));
         CPB_CUDA(cudaMemcpyAsync(hr, P.result, sizeof(ParseResult), cudaMemcpyDeviceToHost, c->stream));
         CPB_CUDA(cudaStreamSynchronize(c->stream));

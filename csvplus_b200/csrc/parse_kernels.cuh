@@ -359,11 +359,11 @@ struct Rec {
 };
 
 // record-level checks in the reference's order: parse error (already set) > field count > missing column
-template <int KMAX>
+template <int KMAX, bool EXACT>
 __device__ __forceinline__ void finish_record(const ParseParams& P, Rec<KMAX>& r) {
     if (r.err != K_OK) return;
     if (P.expect_fields > 0 && r.nf != P.expect_fields) { r.err = K_FIELDS; return; }
-    uint32_t want = (1u << P.nsel) - 1;
+    uint32_t want = (1u << (EXACT ? KMAX : P.nsel)) - 1;
     uint32_t missing = want & ~r.present;
     if (missing) {
         if (P.pad_missing) {  // padded "" values still take part in Like comparisons against empty literals
@@ -377,17 +377,17 @@ __device__ __forceinline__ void finish_record(const ParseParams& P, Rec<KMAX>& r
     }
 }
 
-template <int KMAX>
+template <int KMAX, bool EXACT>
 __device__ __forceinline__ void run_slow(const ParseParams& P, const ByteSrc& src, uint64_t start_abs, Rec<KMAX>& r) {
     SlowOut so;
     slow_record(P, src, start_abs, false, nullptr, nullptr, &so);
     r.err = so.err; r.nf = so.nf; r.present = so.present; r.eq = so.eq; r.slow = true; r.err_slot = 0;
 #pragma unroll
-    for (int k = 0; k < KMAX; k++) r.f[k] = k < P.nsel ? so.ulen[k] : 0;
+    for (int k = 0; k < KMAX; k++) r.f[k] = k < (EXACT ? KMAX : P.nsel) ? so.ulen[k] : 0;
 }
 
 // Line `i` of the window through the flat structural index.  Returns false when it is not a record.
-template <int KMAX>
+template <int KMAX, bool EXACT>
 __device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem& sm, const ByteSrc& src, const uint8_t* lits,
                                           bool lits_in_smem, uint64_t tile_base, int i, int nterm, int rel_n, int64_t rel_ds, bool tile_has_q,
                                           Rec<KMAX>& r) {
@@ -405,14 +405,14 @@ __device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem&
         if (tile_has_q && count_bits(sm.Qb, start, e_nl) != 0) to_slow = true;
     }
     if (to_slow) {
-        run_slow<KMAX>(P, src, tile_base + start, r);
+        run_slow<KMAX, EXACT>(P, src, tile_base + start, r);
     } else {
         const int nf = b - a;
         r.nf = nf;
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
             r.f[k] = 0;
-            if (k < P.nsel) {
+            if (k < (EXACT ? KMAX : P.nsel)) {
                 const int target = P.sel_field[k];
                 if (target < nf) {
                     const int fb = target == 0 ? start : (int)sm.sidx[a + target] + 1;
@@ -433,12 +433,12 @@ __device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem&
             }
         }
     }
-    finish_record<KMAX>(P, r);
+    finish_record<KMAX, EXACT>(P, r);
     return true;
 }
 
 // Dense-tile fallback: the record starting at window offset ws, always through the sequential machine.
-template <int KMAX>
+template <int KMAX, bool EXACT>
 __device__ __forceinline__ bool generic_record(const ParseParams& P, const ParseSmem& sm, const ByteSrc& src, uint64_t tile_base,
                                                int ws, int rel_n, Rec<KMAX>& r) {
     // empty line: "\n", "\r\n", or a lone "\r" right before EOF
@@ -446,8 +446,8 @@ __device__ __forceinline__ bool generic_record(const ParseParams& P, const Parse
     if (c0 == '\n') return false;
     if (c0 == '\r' && (sm.data[PRE + ws + 1] == '\n' || ws + 1 >= rel_n)) return false;
     r.present = 0; r.eq = 0; r.err = K_OK; r.err_slot = 0;
-    run_slow<KMAX>(P, src, tile_base + ws, r);
-    finish_record<KMAX>(P, r);
+    run_slow<KMAX, EXACT>(P, src, tile_base + ws, r);
+    finish_record<KMAX, EXACT>(P, r);
     return true;
 }
 
@@ -551,12 +551,71 @@ __device__ __forceinline__ void lookback_totals(const unsigned long long* words,
     }
 }
 
+// ---- single-warp variants: in steady state the nearest inclusive predecessor is a few tiles back, so one
+// 32-wide round (one L2 round trip) resolves the look-back while the other warps wait at a single barrier.
+__device__ __forceinline__ uint32_t lookback_parity_w0(const uint32_t* st1, uint32_t tile) {
+    const int lane = threadIdx.x & 31;
+    uint32_t acc = 0;
+    int64_t base = (int64_t)tile - 1;
+    for (;;) {
+        const int64_t p = base - lane;
+        uint32_t s = 2u;
+        if (p >= 0) { do { s = ld_relaxed_u32(&st1[p]); } while ((s & 3u) == 0); }
+        const uint32_t incl = __ballot_sync(0xffffffffu, (s & 3u) == 2u);
+        const uint32_t vals = __ballot_sync(0xffffffffu, (s >> 2) & 1u);
+        if (incl) { const int f = __ffs(incl) - 1; acc ^= __popc(vals & (0xffffffffu >> (31 - f))) & 1; break; }
+        acc ^= __popc(vals) & 1;
+        base -= 32;
+    }
+    return acc;
+}
 template <int KMAX>
+__device__ __forceinline__ void lookback_totals_w0(const unsigned long long* words, uint32_t tile, int NP, ParseSmem& sm) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long excl = 0;  // lane c accumulates component c
+    int64_t base = (int64_t)tile - 1;
+    for (;;) {
+        const int64_t p = base - lane;
+        unsigned long long v[KMAX + 2];
+        bool is_incl = true;
+        if (p >= 0) {
+            const unsigned long long* w = words + (uint64_t)p * NP;
+            for (;;) {  // re-read until all words are valid and carry the same status
+#pragma unroll
+                for (int c = 0; c < KMAX + 2; c++) v[c] = c < NP ? ld_relaxed_u64((const uint64_t*)(w + c)) : 0ull;
+                const unsigned long long f0 = v[0] >> 62;
+                bool ok = f0 != 0;
+#pragma unroll
+                for (int c = 1; c < KMAX + 2; c++) if (c < NP) ok = ok && (v[c] >> 62) == f0;
+                if (ok) break;
+            }
+            is_incl = (v[0] >> 62) == 2;
+        } else {
+#pragma unroll
+            for (int c = 0; c < KMAX + 2; c++) v[c] = 0ull;  // before the first tile: inclusive zero
+        }
+        const uint32_t incl = __ballot_sync(0xffffffffu, is_incl);
+        const int f = __ffs(incl) - 1;
+        const bool take = p >= 0 && (f < 0 || lane <= f);
+#pragma unroll
+        for (int c = 0; c < KMAX + 2; c++) {
+            if (c < NP) {
+                const unsigned long long x = warp_sum_u64(take ? (v[c] & LB_VAL) : 0ull);
+                if (lane == c) excl += x;
+            }
+        }
+        if (f >= 0) break;
+        base -= 32;
+    }
+    if (lane < NP) sm.tile_prefix[lane] = excl;
+}
+
+template <int KMAX, bool EXACT>
 __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ParseSmem& sm = *reinterpret_cast<ParseSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NP = 2 + P.nsel;
+    const int NP = 2 + (EXACT ? KMAX : P.nsel);
     const uint32_t NL4 = 0x0a0a0a0au, Q4 = 0x22222222u, D4 = P.delim * 0x01010101u;
 
     if (tid == 0) { mbar_init(&sm.mbar, 1); fence_mbar_init(); }
@@ -629,9 +688,13 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
         uint32_t pin = 0;
         bool pin_known = tile == 0;
         if (hasq && !pin_known) {
-            pin = lookback_parity(P.st1, tile, sm);
+            if (warp == 0) {
+                const uint32_t pv = lookback_parity_w0(P.st1, tile);
+                if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
+            }
+            __syncthreads();
+            pin = sm.pin;
             pin_known = true;
-            if (tid == 0) st_release_u32(&P.st1[tile], 2u | ((pin ^ tile_par) << 2));
         }
     retry:
         if (hasq || pin) {
@@ -677,25 +740,28 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
 #pragma unroll
             for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) ex += t; tile_tot += t; }
             uint32_t o = ex & 0xffffu, tc = ex >> 16;
-#pragma unroll
-            for (int j = 0; j < WPT; j++) {
-                uint32_t m = sws[j];
-                const int pos0 = (tid * WPT + j) * 32;
-                uint32_t tm = tws[j];
-                while (tm) {  // terminators are ~7x sparser than structurals: their ordinals come from a popcount
-                    int bpos = __ffs(tm) - 1; tm &= tm - 1;
-                    if (tc < LCAP) sm.ord[tc] = (uint16_t)(o + __popc(m & ((1u << bpos) - 1)));
-                    tc++;
-                }
-                while (m) {
-                    int bpos = __ffs(m) - 1; m &= m - 1;
-                    if (o < SCAP) sm.sidx[o] = (uint16_t)(pos0 + bpos);
-                    o++;
-                }
-            }
             uint32_t halo_tot = 0;
             for (int i = 0; i < HALO_WORDS / 32; i++) halo_tot += sm.wtot[1][i];
-            if (tid < HALO_WORDS) {
+            // the totals are known before the expansion: a window that does not fit skips it (dense fallback), one
+            // that fits needs no bounds checks
+            const bool fits = (tile_tot & 0xffffu) + (halo_tot & 0xffffu) <= (uint32_t)SCAP && (tile_tot >> 16) + (halo_tot >> 16) <= (uint32_t)LCAP;
+            if (fits) {
+#pragma unroll
+                for (int j = 0; j < WPT; j++) {
+                    uint32_t m = sws[j];
+                    const int pos0 = (tid * WPT + j) * 32;
+                    uint32_t tm = tws[j];
+                    while (tm) {  // terminators are ~7x sparser than structurals: their ordinals come from a popcount
+                        int bpos = __ffs(tm) - 1; tm &= tm - 1;
+                        sm.ord[tc++] = (uint16_t)(o + __popc(m & ((1u << bpos) - 1)));
+                    }
+                    while (m) {
+                        int bpos = __ffs(m) - 1; m &= m - 1;
+                        sm.sidx[o++] = (uint16_t)(pos0 + bpos);
+                    }
+                }
+            }
+            if (fits && tid < HALO_WORDS) {
                 uint32_t hex = hinc - hv;
                 for (int i = 0; i < warp; i++) hex += sm.wtot[1][i];
                 uint32_t o2 = (tile_tot & 0xffffu) + (hex & 0xffffu), tc2 = (tile_tot >> 16) + (hex >> 16);
@@ -703,8 +769,8 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 const int pos0 = (TILE_WORDS + tid) * 32;
                 while (m) {
                     int bpos = __ffs(m) - 1; m &= m - 1;
-                    if (o2 < SCAP) sm.sidx[o2] = (uint16_t)(pos0 + bpos);
-                    if ((ht >> bpos) & 1) { if (tc2 < LCAP) sm.ord[tc2] = (uint16_t)o2; tc2++; }
+                    sm.sidx[o2] = (uint16_t)(pos0 + bpos);
+                    if ((ht >> bpos) & 1) sm.ord[tc2++] = (uint16_t)o2;
                     o2++;
                 }
             }
@@ -759,7 +825,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 nrow++;
                 survived = true;
 #pragma unroll
-                for (int k = 0; k < KMAX; k++) if (k < P.nsel) cb[k] += r.slow ? r.f[k] : (r.f[k] >> 16);
+                for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) cb[k] += r.slow ? r.f[k] : (r.f[k] >> 16);
             }
             nrec++;
             return survived;
@@ -777,7 +843,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 const int i = i0 + tid * L + q;
                 if (q < L && i <= m_last) {
                     Rec<KMAX> r;
-                    if (flat_line<KMAX>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
+                    if (flat_line<KMAX, EXACT>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
                         const bool surv = account(r);
                         if (r.slow) any_slow = true;
                         else if (surv) {
@@ -792,7 +858,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 const int i = i0 + tid * L + q;
                 if (i > m_last) break;
                 Rec<KMAX> r;
-                if (flat_line<KMAX>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
+                if (flat_line<KMAX, EXACT>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
             }
         } else {
 #pragma unroll 1
@@ -801,14 +867,18 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 while (m) {
                     int b = __ffs(m) - 1; m &= m - 1;
                     Rec<KMAX> r;
-                    if (generic_record<KMAX>(P, sm, src, tile_base, (tid * WPT + j) * 32 + b, rel_n, r)) account(r);
+                    if (generic_record<KMAX, EXACT>(P, sm, src, tile_base, (tid * WPT + j) * 32 + b, rel_n, r)) account(r);
                 }
             }
         }
         if (!pin_known) {  // verify the optimistic assumption "this tile starts outside quotes"
-            pin = lookback_parity(P.st1, tile, sm);
+            if (warp == 0) {
+                const uint32_t pv = lookback_parity_w0(P.st1, tile);
+                if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
+            }
+            __syncthreads();
+            pin = sm.pin;
             pin_known = true;
-            if (tid == 0) st_release_u32(&P.st1[tile], 2u | ((pin ^ tile_par) << 2));
             if (pin) goto retry;
         }
         // staged output (coalesced stores) needs every row of the tile cached and on the fast path
@@ -818,11 +888,11 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
         uint32_t i0s = warp_incl_scan(v0);
         uint32_t ik[KMAX];
 #pragma unroll
-        for (int k = 0; k < KMAX; k++) if (k < P.nsel) ik[k] = warp_incl_scan(cb[k]);
+        for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) ik[k] = warp_incl_scan(cb[k]);
         if (lane == 31) {
             sm.wtot[0][warp] = i0s;
 #pragma unroll
-            for (int k = 0; k < KMAX; k++) if (k < P.nsel) sm.wtot[1 + k][warp] = ik[k];
+            for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) sm.wtot[1 + k][warp] = ik[k];
         }
         __syncthreads();
         uint32_t ex0 = i0s - v0, tot0 = 0;
@@ -832,7 +902,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
             exk[k] = 0; totk[k] = 0;
-            if (k < P.nsel) {
+            if (k < (EXACT ? KMAX : P.nsel)) {
                 exk[k] = ik[k] - cb[k];
 #pragma unroll
                 for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[1 + k][i]; if (i < warp) exk[k] += t; totk[k] += t; }
@@ -852,8 +922,11 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 __syncthreads();
             } else {
                 if (tid < NP) st_relaxed_u64((uint64_t*)(wt + tid), LB_AGG | mine);
-                lookback_totals<KMAX>(P.words, tile, NP, sm);
-                if (tid < NP) st_relaxed_u64((uint64_t*)(wt + tid), LB_INCL | (sm.tile_prefix[tid] + mine));
+                if (warp == 0) {
+                    lookback_totals_w0<KMAX>(P.words, tile, NP, sm);
+                    if (lane < NP) st_relaxed_u64((uint64_t*)(wt + lane), LB_INCL | (sm.tile_prefix[lane] + mine));
+                }
+                __syncthreads();
             }
             if (tile == P.ntiles - 1 && tid < NP) {  // totals + end-of-column sentinels
                 const unsigned long long total = sm.tile_prefix[tid] + mine;
@@ -891,7 +964,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 if (nrow != 0 && row == 0) P.result->first_row_ordinal = rec0 + first_surv_rec;
 #pragma unroll
                 for (int k = 0; k < KMAX; k++) {
-                    if (k < P.nsel) {
+                    if (k < (EXACT ? KMAX : P.nsel)) {
                         const uint64_t dbase = sm.tile_prefix[2 + k];
                         {
                             uint32_t j = ex0 >> 16, run = exk[k];
@@ -905,9 +978,14 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                             uint32_t* gout = P.out_off[k] + (row_base - osh);
                             const uint64_t rows_ok = P.row_cap > row_base ? P.row_cap - row_base : 0;  // rows of this tile that fit
                             const uint32_t lim_e = osh + (uint32_t)(tile_rows < rows_ok ? tile_rows : rows_ok);
-                            for (uint32_t e = tid * 4; e < lim_e; e += THREADS * 4) {
+                            for (uint32_t e = tid * 4; e < lim_e; e += THREADS * 4)
                                 if (e >= osh && e + 4 <= lim_e) *reinterpret_cast<uint4*>(gout + e) = *reinterpret_cast<const uint4*>(ost + e);
-                                else for (uint32_t x = e; x < e + 4; x++) if (x >= osh && x < lim_e) gout[x] = ost[x];
+                            if (tid < 8) {  // partial first / last vector: one element per lane
+                                const uint32_t tv0 = lim_e & ~3u;
+                                const uint32_t x = tid < 4 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 4);
+                                const bool head = tid < 4 && osh != 0;
+                                const bool tail = tid >= 4 && (lim_e & 3u) != 0 && !(tv0 == 0 && osh != 0);
+                                if ((head || tail) && x >= osh && x < lim_e) gout[x] = ost[x];
                             }
                         }
                         // ---- field bytes
@@ -926,9 +1004,15 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                             }
                             __syncthreads();
                             const uint32_t cend = c0 + CH < r16 + B ? c0 + CH : r16 + B;
-                            for (uint32_t x0 = c0 + tid * 16; x0 < cend; x0 += THREADS * 16) {
+                            for (uint32_t x0 = c0 + tid * 16; x0 < cend; x0 += THREADS * 16)
                                 if (x0 >= r16 && x0 + 16 <= hi_ok) *reinterpret_cast<uint4*>(gbase + x0) = *reinterpret_cast<const uint4*>(stage + (x0 - c0));
-                                else for (uint32_t x = x0; x < x0 + 16; x++) if (x >= r16 && x < hi_ok) gbase[x] = stage[x - c0];
+                            // the (at most two) partial vectors at the column's first and last byte: one byte per lane
+                            if (tid < 32) {
+                                const uint32_t tv0 = hi_ok & ~15u;
+                                const uint32_t x = tid < 16 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 16);
+                                const bool head = tid < 16 && c0 == 0 && r16 != 0;
+                                const bool tail = tid >= 16 && (hi_ok & 15u) != 0 && tv0 >= c0 && tv0 < cend && !(tv0 == 0 && r16 != 0);
+                                if ((head || tail) && x >= r16 && x < hi_ok) gbase[x] = stage[x - c0];
                             }
                             __syncthreads();
                         }
@@ -938,7 +1022,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
             } else if (nrow != 0) {
                 uint64_t off[KMAX];
 #pragma unroll
-                for (int k = 0; k < KMAX; k++) off[k] = k < P.nsel ? sm.tile_prefix[2 + k] + exk[k] : 0;
+                for (int k = 0; k < KMAX; k++) off[k] = k < (EXACT ? KMAX : P.nsel) ? sm.tile_prefix[2 + k] + exk[k] : 0;
                 uint32_t rec_local = 0;
                 auto emit = [&](const Rec<KMAX>& r, uint64_t start_abs) {
                     if (r.err != K_OK || !eval_pred(P.pred, r.eq)) { rec_local++; return; }
@@ -954,7 +1038,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                     }
 #pragma unroll
                     for (int k = 0; k < KMAX; k++) {
-                        if (k < P.nsel) {
+                        if (k < (EXACT ? KMAX : P.nsel)) {
                             uint32_t len = r.slow ? r.f[k] : (r.f[k] >> 16);
                             if (row_ok) P.out_off[k][row] = (uint32_t)off[k];
                             if (!r.slow && off[k] + len <= P.data_cap[k]) {
@@ -972,7 +1056,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                         const int i = i0 + tid * L + q;
                         if (i > m_last) break;
                         Rec<KMAX> r;
-                        if (flat_line<KMAX>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
+                        if (flat_line<KMAX, EXACT>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
                             emit(r, tile_base + (i == 0 ? 0 : (uint64_t)sm.sidx[sm.ord[i - 1]] + 1));
                     }
                 } else {
@@ -983,7 +1067,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                             int b = __ffs(m) - 1; m &= m - 1;
                             const int ws = (tid * WPT + j) * 32 + b;
                             Rec<KMAX> r;
-                            if (generic_record<KMAX>(P, sm, src, tile_base, ws, rel_n, r)) emit(r, tile_base + ws);
+                            if (generic_record<KMAX, EXACT>(P, sm, src, tile_base, ws, rel_n, r)) emit(r, tile_base + ws);
                         }
                     }
                 }
