@@ -82,14 +82,17 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
         fail(CPB_E_INVALID_DELIM, -1, 1, "csv: invalid field or comment delimiter");
         return empty_table(spec_names);
     }
-    if (o.comment != 0 || o.lazy_quotes || o.trim_leading_space || o.delimiter >= 0x80)
-        throw ArgError{CPB_ERR_UNSUPPORTED,
-                       "CommentChar / LazyQuotes / TrimLeadingSpace / multi-byte Delimiter are not lowered to kernels yet"};
+    if (o.delimiter >= 0x80 || o.comment >= 0x80)
+        throw ArgError{CPB_ERR_UNSUPPORTED, "multi-byte Delimiter / CommentChar runes are not lowered to kernels yet"};
+    // CommentChar / LazyQuotes / TrimLeadingSpace change what "inside quotes" means: they take the general
+    // (DFA-composition, multi-pass) path of parse_general.cu; the default options take the single-pass scan.
+    const bool general = o.comment != 0 || o.lazy_quotes || o.trim_leading_space;
     if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) throw ArgError{CPB_ERR_ARG, "device input must be 16-byte aligned"};
 
     // ---- header kernel (first record + sampling)
     Buf hbuf = dev_alloc(c, sizeof(HeaderOut));
-    {
+    if (general) general_header(c, in, n, o, hbuf->as<HeaderOut>());
+    else {
         KernelTimer kt(c, "csv_header", 0);
         csv_header_kernel<<<1, 256, 0, c->stream>>>(in, n, (int)o.delimiter, hbuf->as<HeaderOut>());
         CPB_CUDA(cudaGetLastError());
@@ -187,6 +190,27 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
         CPB_CUDA(cudaMemcpyAsync(lits->p, comp.lits.data(), comp.lits.size(), cudaMemcpyHostToDevice, c->stream));
     P.lits = lits->as<uint8_t>();
     P.lits_len = (uint32_t)comp.lits.size();
+
+    if (general) {
+        GenResult gr;
+        general_parse(c, P, o, data_start, &gr);
+        auto t = std::make_shared<Table>();
+        t->ctx = c; t->nrows = (int64_t)gr.rows; t->first_line = line_base;
+        if (gr.err_key != ~0ull) {
+            uint64_t ordinal = gr.err_key >> 16;
+            int kind = (int)((gr.err_key >> 8) & 0xff), slot = (int)(gr.err_key & 0xff);
+            if (kind == CPB_E_COLUMN_INDEX) {
+                int ci = 0;
+                for (size_t i = 0; i < cols.size(); i++) if (col_slot[i] == slot) { ci = (int)i; break; }
+                fail(kind, ci, line_base + ordinal, "column not found: " + go_quote(cols[ci].first) + " (" + std::to_string(cols[ci].second) + ")");
+            } else fail(kind, -1, line_base + ordinal, kind_text(kind));
+        }
+        for (size_t i = 0; i < cols.size(); i++) {
+            Column col; col.name = cols[i].first; col.offsets = gr.offs[col_slot[i]]; col.data = gr.datas[col_slot[i]];
+            t->cols.push_back(col);
+        }
+        return t;
+    }
 
     // ---- capacities (exact totals always come back; overflow => one exact rerun)
     const int NP = 2 + nsel;

@@ -190,3 +190,64 @@ def test_full_size_properties():
     nbytes = C.c_uint64()
     ctx.lib.cpb_table_col_bytes(ctx.h, t.h, 0, 0, n, C.byref(nbytes))
     assert nbytes.value == nb
+
+
+# ------------------------------------------------------------------ general reader options (parse_general.cu)
+def _general_opts(o):
+    return (o.comment or o.lazy_quotes or o.trim_leading_space) and ord(o.comma) < 0x80 and (not o.comment or ord(o.comment) < 0x80)
+
+
+@pytest.mark.parametrize("i", [i for i, k in enumerate(KATS) if _general_opts(k[1])])
+def test_kat_vectors_general_options(i):
+    """SURVEY App. A.3 vectors that use CommentChar / LazyQuotes / TrimLeadingSpace"""
+    data, opts, _, _ = KATS[i]
+    check_parity(data, opts=opts)
+    check_parity(data, opts=orc.Opts(**{**opts.__dict__, "fields_per_record": -1}), assume={"a": 0, "b": 1, "c": 2, "d": 3})
+
+
+def _mutate(data: bytes, seed: int, comments=False, stray_quotes=False, spaces=False) -> bytes:
+    import random
+    rng = random.Random(seed)
+    out = bytearray()
+    for ln in data.split(b"\n"):
+        if comments and rng.random() < 0.15:
+            out += b"#" + rng.choice([b' a "comment" line', b'"unbalanced', b"", b"x,y,z"]) + rng.choice([b"\n", b"\r\n"])
+        if spaces and ln:
+            ln = b",".join(rng.choice([b"", b" ", b"\t ", b"  "]) + f for f in ln.split(b","))
+        if stray_quotes and ln and rng.random() < 0.3:
+            p = rng.randrange(len(ln) + 1)
+            ln = ln[:p] + b'"' + ln[p:]
+        out += ln + b"\n"
+    return bytes(out[:-1])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_general_options(seed):
+    base = random_csv(300 + seed, nrows=1500, ncols=4, quoted_p=0.35, crlf_p=0.3, blank_p=0.1)
+    # comment lines (may contain quotes), default quote rules
+    d1 = _mutate(base, seed, comments=True)
+    check_parity(d1, opts=orc.Opts(comment="#"))
+    check_parity(d1, opts=orc.Opts(comment="#"), select=["c2", "c0"])
+    # lazy quotes: stray quotes anywhere never fail; field counts still checked
+    d2 = _mutate(base, seed, stray_quotes=True)
+    check_parity(d2, opts=orc.Opts(lazy_quotes=True, fields_per_record=-1))
+    check_parity(d2, opts=orc.Opts(lazy_quotes=True))
+    check_parity(d2, opts=orc.Opts())  # the same bytes under strict rules: first error must agree
+    # leading white space, with and without trimming; all three options together
+    d3 = _mutate(base, seed, spaces=True)
+    check_parity(d3, opts=orc.Opts(trim_leading_space=True, fields_per_record=-1))
+    check_parity(d3, opts=orc.Opts(fields_per_record=-1))
+    d4 = _mutate(base, seed, comments=True, stray_quotes=True, spaces=True)
+    check_parity(d4, opts=orc.Opts(comment="#", lazy_quotes=True, trim_leading_space=True, fields_per_record=-1), select=["c1", "c3"],
+                 like={"c1": ""})
+    check_parity(d4, opts=orc.Opts(comment="#", lazy_quotes=True, trim_leading_space=True))
+
+
+def test_general_options_big_and_edges():
+    big = random_csv(77, nrows=40000, ncols=5, quoted_p=0.3, long_p=0.002, crlf_p=0.2)
+    check_parity(_mutate(big, 1, comments=True), opts=orc.Opts(comment="#"))
+    for data in [b"", b"#only comment", b"#c\n\n#d\r\n", b"a,b\n#x\n1,2\n", b" a , b \n 1, \"q\" \n", b'a\n"x\r', b"\r", b"a,b\r\n\r\n#z\r\n1,2"]:
+        for o in (orc.Opts(comment="#"), orc.Opts(lazy_quotes=True), orc.Opts(trim_leading_space=True),
+                  orc.Opts(comment="#", lazy_quotes=True, trim_leading_space=True)):
+            check_parity(data, opts=o)
+            check_parity(data, opts=orc.Opts(**{**o.__dict__, "fields_per_record": -1}), assume={"x": 0, "y": 1})
