@@ -87,6 +87,8 @@ struct HashTable {
     uint64_t nheads = 0;     // distinct key prefixes
     Buf slots;               // uint32 head ordinal or 0xFFFFFFFF (open addressing, linear probing)
     Buf heads;               // uint32[nheads+1]: sorted position of each distinct prefix; heads[nheads] = nrows
+    uint64_t nslots32 = 0;   // embedded-key table (prefix <= 24 bytes, table too large for shared memory)
+    Buf slots32;             // 32-byte slots: 3 key words + (first row | run length << 32)
 };
 struct Index {
     Ctx* ctx = nullptr;
@@ -160,6 +162,16 @@ std::shared_ptr<Table> concat_tables(Ctx* c, const std::vector<const Table*>& pa
 // sort.cu
 std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std::string>& keys, bool unique,
                                    DataError* derr, bool* failed);
+constexpr int MAXKEYS = 16;
+struct KeyDesc {  // key columns + the widths of the order-preserving image (sort.cu)
+    int nkeys;
+    const uint32_t* off[MAXKEYS];
+    const uint8_t* data[MAXKEYS];
+    uint32_t width[MAXKEYS];     // bytes of value kept
+    uint32_t lenbytes[MAXKEYS];  // bytes of the big-endian length field
+    uint32_t words;              // image words per row
+};
+void describe_keys(Ctx* c, const Table& t, const std::vector<int>& kidx, const std::vector<uint32_t>& width, KeyDesc& kd);
 uint32_t prefix_bytes(const Index& ix, int nk);  // image bytes covered by the first nk key columns
 Buf pack_with_widths(Ctx* c, const Table& t, const std::vector<int>& kidx, const std::vector<uint32_t>& width, uint32_t* words_out);
 // join.cu

@@ -96,6 +96,66 @@ __global__ void __launch_bounds__(256) join_probe_kernel(const uint64_t* __restr
     }
 }
 
+// ------------------------------------------------------------------ embedded-key table (key prefixes <= 24 bytes)
+// One 32-byte slot = one DRAM sector: the whole key prefix (3 image words) + (first sorted row, run length).
+// A probe is resolved by the sector it hashes to — no dependent reads of heads[] / the key image — and the probe
+// key is packed in registers straight from the probe column (no materialised probe image).
+struct __align__(32) Slot32 { unsigned long long k[3]; unsigned long long payload; };  // payload = lo | cnt << 32; 0 = empty
+
+__device__ __forceinline__ uint64_t hash3(unsigned long long a, unsigned long long b, unsigned long long c) {
+    return mix64(mix64(mix64(0x9E3779B97F4A7C15ull ^ a) ^ b) ^ c);
+}
+__device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t nslots) { return __umul64hi(h, nslots); }
+
+__global__ void hash32_insert_kernel(const uint64_t* __restrict__ image, uint64_t n, uint32_t pbytes, const uint32_t* __restrict__ heads,
+                                     uint64_t nheads, Slot32* slots, uint64_t nslots) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nheads) return;
+    const uint32_t r = heads[j], full = pbytes >> 3, rem = pbytes & 7;
+    unsigned long long w[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < full; i++) w[i] = image[(uint64_t)i * n + r];
+    if (rem) w[full] = image[(uint64_t)full * n + r] & (~0ull << (8 * (8 - rem)));
+    const unsigned long long payload = (unsigned long long)r | ((unsigned long long)(heads[j + 1] - r) << 32);
+    uint64_t s = slot_of(hash3(w[0], w[1], w[2]), nslots);
+    for (;;) {
+        if (atomicCAS(&slots[s].payload, 0ull, payload) == 0ull) { slots[s].k[0] = w[0]; slots[s].k[1] = w[1]; slots[s].k[2] = w[2]; return; }
+        if (++s == nslots) s = 0;
+    }
+}
+
+// packs the probe key exactly like key_pack_kernel (sort.cu), but into three registers
+__device__ __forceinline__ void pack3(const KeyDesc& kd, uint64_t r, unsigned long long& w0, unsigned long long& w1, unsigned long long& w2) {
+    unsigned long long cur = 0; int cnt = 0, word = 0;
+    w0 = w1 = w2 = 0;
+    auto flush = [&](unsigned long long v) { if (word == 0) w0 = v; else if (word == 1) w1 = v; else w2 = v; word++; };
+    auto push = [&](uint32_t b) { cur = (cur << 8) | b; if (++cnt == 8) { flush(cur); cnt = 0; cur = 0; } };
+    for (int k = 0; k < kd.nkeys; k++) {
+        const uint32_t s = kd.off[k][r], len = kd.off[k][r + 1] - s, wd = kd.width[k];
+        const uint8_t* p = kd.data[k] + s;
+        for (uint32_t i = 0; i < wd; i++) push(i < len ? p[i] : 0u);
+        const uint32_t lf = len > wd ? 0xffffffffu : len;
+        for (int i = (int)kd.lenbytes[k] - 1; i >= 0; i--) push((lf >> (8 * i)) & 0xffu);
+    }
+    if (cnt) flush(cur << (8 * (8 - cnt)));
+}
+__global__ void __launch_bounds__(256) join_probe32_kernel(KeyDesc kd, uint64_t np, const Slot32* __restrict__ slots, uint64_t nslots,
+                                                           uint32_t* lo, uint32_t* cnt, uint32_t* not_one) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long w0, w1, w2;
+        pack3(kd, i, w0, w1, w2);
+        uint64_t s = slot_of(hash3(w0, w1, w2), nslots);
+        uint32_t l = 0, c = 0;
+        for (;;) {
+            const ulonglong4 sl = *reinterpret_cast<const ulonglong4*>(&slots[s]);  // one 32-byte sector
+            if (sl.w == 0ull) break;
+            if (sl.x == w0 && sl.y == w1 && sl.z == w2) { l = (uint32_t)sl.w; c = (uint32_t)(sl.w >> 32); break; }
+            if (++s == nslots) s = 0;
+        }
+        lo[i] = l; cnt[i] = c;
+        if (c != 1) *not_one = 1u;  // benign race: every writer stores 1
+    }
+}
+
 __global__ void expand_pairs_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ pos,
                                     uint32_t* pid, uint32_t* iid, uint64_t np) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,6 +205,15 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
                                                                         ht.slots->as<uint32_t>(), ht.nslots - 1);
         CPB_CUDA(cudaGetLastError());
     }
+    if (ht.pbytes <= 24 && (ht.nslots + ht.nheads + 1) * 4 > 200 * 1024) {  // too large for smem, key fits a sector
+        ht.nslots32 = ht.nheads + ht.nheads / 2 + 16;
+        ht.slots32 = dev_alloc(c, ht.nslots32 * sizeof(Slot32));
+        CPB_CUDA(cudaMemsetAsync(ht.slots32->p, 0, ht.nslots32 * sizeof(Slot32), c->stream));
+        KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8) + ht.nslots32 * 32);
+        hash32_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
+                                                                          ht.slots32->as<Slot32>(), ht.nslots32);
+        CPB_CUDA(cudaGetLastError());
+    }
     return ix.hash.emplace(nk, std::move(ht)).first->second;
 }
 
@@ -185,12 +254,19 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
         HashTable& ht = ensure_hash(c, ix, nk);
         std::vector<uint32_t> widths(ix.key_width.begin(), ix.key_width.begin() + nk);
         uint32_t pwords = 0;
-        Buf pimg = pack_with_widths(c, probe, pidx, widths, &pwords);
+        Buf pimg;
+        if (!ht.slots32) pimg = pack_with_widths(c, probe, pidx, widths, &pwords);
+        else pwords = (ht.pbytes + 7) / 8;
         // algorithmic bytes: probe keys once + build table once
         uint64_t algo = np * ((uint64_t)pwords * 8 + 8) + ht.nslots * 4 + ht.nheads * ((uint64_t)ht.pbytes + 4);
         size_t smem = (ht.nslots + ht.nheads + 1) * 4;
         KernelTimer kt(c, "join_probe", algo);
-        if (smem <= 200 * 1024) {
+        if (ht.slots32) {
+            KeyDesc kd{};
+            describe_keys(c, probe, pidx, widths, kd);
+            uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
+            join_probe32_kernel<<<grid, 256, 0, c->stream>>>(kd, np, ht.slots32->as<Slot32>(), ht.nslots32, lo->as<uint32_t>(), cnt->as<uint32_t>(), not_one);
+        } else if (smem <= 200 * 1024) {
             static bool configured = false;
             if (!configured) { CPB_CUDA(cudaFuncSetAttribute(join_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
             uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count);

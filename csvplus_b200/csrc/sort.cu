@@ -16,17 +16,8 @@
 
 namespace cpb {
 
-constexpr int MAXKEYS = 16;
 static inline uint32_t nblk(uint64_t n, int t) { return (uint32_t)((n + t - 1) / t); }
 
-struct KeyDesc {
-    int nkeys;
-    const uint32_t* off[MAXKEYS];
-    const uint8_t* data[MAXKEYS];
-    uint32_t width[MAXKEYS];     // bytes of value kept
-    uint32_t lenbytes[MAXKEYS];  // bytes of the big-endian length field
-    uint32_t words;              // image words per row
-};
 
 // ------------------------------------------------------------------ key widths
 __global__ void max_len_kernel(const uint32_t* __restrict__ off, uint64_t n, uint32_t* out) {
@@ -236,7 +227,7 @@ static uint64_t read_u64(Ctx* c, const void* dev) {
     return *h;
 }
 
-static void describe_keys(Ctx* c, const Table& t, const std::vector<int>& kidx, const std::vector<uint32_t>& width, KeyDesc& kd) {
+void describe_keys(Ctx* c, const Table& t, const std::vector<int>& kidx, const std::vector<uint32_t>& width, KeyDesc& kd) {
     kd.nkeys = (int)kidx.size();
     uint32_t bytes = 0;
     for (int k = 0; k < kd.nkeys; k++) {
