@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcsvplus_b200.so")
+LIB_PATH = os.environ.get("CPB_LIB", os.path.join(HERE, "libcsvplus_b200.so"))  # CPB_LIB: A/B builds of the same ABI
 
 
 class Str(C.Structure):

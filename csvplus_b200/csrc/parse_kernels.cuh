@@ -635,9 +635,11 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
     const uint8_t* lits = lits_in_smem ? sm.lits : P.lits;
     __syncthreads();
     uint32_t phase = 0;
+    // thread 0 draws the next tile's ticket in the middle of the current tile, so the atomic's round trip is hidden
+    uint32_t next_ticket = tid == 0 ? atomicAdd(P.ticket, 1u) : 0u;
 
     for (;;) {
-        if (tid == 0) sm.ticket = atomicAdd(P.ticket, 1u);
+        if (tid == 0) sm.ticket = next_ticket;
         __syncthreads();
         const uint32_t tile = sm.ticket;
         if (tile >= P.ntiles) break;
@@ -892,6 +894,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
             pin_known = true;
             if (pin) goto retry;
         }
+        if (tid == 0) next_ticket = atomicAdd(P.ticket, 1u);
         // staged output (coalesced stores) needs every row of the tile cached and on the fast path
         const bool staged_pre = !__syncthreads_or(any_slow) && flat_ok && L <= RC;
         // ---- block scan of (records | rows << 16, bytes[k])
@@ -1011,7 +1014,15 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                                 const uint32_t st = ost[osh + j] - (uint32_t)dbase + r16;  // shifted tile-local start
                                 const uint32_t lo = st > c0 ? st : c0, hi = st + len < c0 + CH ? st + len : c0 + CH;
                                 const uint8_t* sp = sm.data + PRE + (f & 0xffffu) - st;
-                                for (uint32_t x = lo; x < hi; x++) stage[x - c0] = sp[x];
+                                // bytes up to the next aligned staging word, then whole words (source re-aligned by a funnel
+                                // shift of two aligned shared-memory words), then the tail bytes
+                                uint32_t x = lo;
+#ifndef CPB_BYTE_COPY
+                                for (; x < hi && ((x - c0) & 3u); x++) stage[x - c0] = sp[x];
+                                const uint32_t sbase = PRE + (f & 0xffffu) - st;  // sm.data offset of shifted position 0 of this field
+                                for (; x + 4 <= hi; x += 4) *reinterpret_cast<uint32_t*>(stage + (x - c0)) = lds_u32_at(sm.data, sbase + x);
+#endif
+                                for (; x < hi; x++) stage[x - c0] = sp[x];
                             }
                             __syncthreads();
                             const uint32_t cend = c0 + CH < r16 + B ? c0 + CH : r16 + B;
