@@ -19,6 +19,12 @@
 #include "pred.cuh"
 #include "util.cuh"
 
+// A/B switches measured on B200 (tools/time_parse.py, 20 M rows): drawing the next tile's ticket early lengthens the
+// look-back distance (656 vs 720 GB/s); word-wise staging copies lose to the byte loop on short fields (510 vs 528 GB/s).
+#ifndef CPB_EARLY_TICKET
+#define CPB_LATE_TICKET 1
+#endif
+
 namespace cpb {
 
 constexpr int TILE = 32768;
@@ -636,10 +642,18 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
     __syncthreads();
     uint32_t phase = 0;
     // thread 0 draws the next tile's ticket in the middle of the current tile, so the atomic's round trip is hidden
+#ifdef CPB_LATE_TICKET
+    uint32_t next_ticket = 0; (void)next_ticket;
+#else
     uint32_t next_ticket = tid == 0 ? atomicAdd(P.ticket, 1u) : 0u;
+#endif
 
     for (;;) {
+#ifdef CPB_LATE_TICKET
+        if (tid == 0) sm.ticket = atomicAdd(P.ticket, 1u);
+#else
         if (tid == 0) sm.ticket = next_ticket;
+#endif
         __syncthreads();
         const uint32_t tile = sm.ticket;
         if (tile >= P.ntiles) break;
@@ -894,7 +908,9 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
             pin_known = true;
             if (pin) goto retry;
         }
+#ifndef CPB_LATE_TICKET
         if (tid == 0) next_ticket = atomicAdd(P.ticket, 1u);
+#endif
         // staged output (coalesced stores) needs every row of the tile cached and on the fast path
         const bool staged_pre = !__syncthreads_or(any_slow) && flat_ok && L <= RC;
         // ---- block scan of (records | rows << 16, bytes[k])
@@ -1017,7 +1033,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                                 // bytes up to the next aligned staging word, then whole words (source re-aligned by a funnel
                                 // shift of two aligned shared-memory words), then the tail bytes
                                 uint32_t x = lo;
-#ifndef CPB_BYTE_COPY
+#ifdef CPB_WORD_COPY
                                 for (; x < hi && ((x - c0) & 3u); x++) stage[x - c0] = sp[x];
                                 const uint32_t sbase = PRE + (f & 0xffffu) - st;  // sm.data offset of shifted position 0 of this field
                                 for (; x + 4 <= hi; x += 4) *reinterpret_cast<uint32_t*>(stage + (x - c0)) = lds_u32_at(sm.data, sbase + x);
