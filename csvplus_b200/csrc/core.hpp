@@ -98,7 +98,8 @@ struct Index {
     std::vector<uint32_t> key_width;   // per key column: max value length (bytes) in this index
     uint32_t image_words = 0;          // uint64 words per row of the key image
     Buf image;                         // uint64[image_words][nrows] (word-major / SoA)
-    std::map<int, HashTable> hash;     // by number of leading key columns
+    std::map<int, HashTable> hash;     // by number of leading key columns (built lazily, under `mu`)
+    std::mutex mu;                     // several contexts may probe one index concurrently
 };
 
 // ------------------------------------------------------------------ kernel stats

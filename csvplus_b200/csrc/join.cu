@@ -180,6 +180,7 @@ static uint64_t read_u64(Ctx* c, const void* dev) {
 }
 
 static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
+    std::lock_guard<std::mutex> lk(ix.mu);
     auto it = ix.hash.find(nk);
     if (it != ix.hash.end()) return it->second;
     HashTable ht;
@@ -214,6 +215,7 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
                                                                           ht.slots32->as<Slot32>(), ht.nslots32);
         CPB_CUDA(cudaGetLastError());
     }
+    CPB_CUDA(cudaStreamSynchronize(c->stream));  // complete before any other context (stream) can find it in the map
     return ix.hash.emplace(nk, std::move(ht)).first->second;
 }
 
