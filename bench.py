@@ -199,15 +199,32 @@ def main():
 
     from csvplus_b200.dist import allgather_table
 
+    dbg = bool(os.environ.get("BENCH_DEBUG")) and rank == 0
+
     def join_step(cust_src, orders_src):
+        marks = []
+
+        def mark(name):
+            if dbg:
+                ctx.sync(); torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+        mark("start")
         tc, err = cp.parse_csv(ctx, cust_src, spec=CUST_COLS)
         assert err is None
+        mark("parse_cust")
         if world > 1:
             tc = allgather_table(ctx, tc, dist)
+            mark("allgather")
         idx = tc.index_on("id", unique=True)
+        mark("index")
         to, err = cp.parse_csv(ctx, orders_src, spec=ORDER_COLS)
         assert err is None
+        mark("parse_orders")
         j = to.join(idx, "cust_id")
+        mark("join")
+        if dbg:
+            print("phases(ms): " + " ".join("%s=%.2f" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3)
+                                           for i in range(1, len(marks))), file=sys.stderr)
         return j
 
     def parse_step(people_src):

@@ -90,6 +90,15 @@ struct HashTable {
     uint64_t nslots32 = 0;   // embedded-key table (prefix <= 24 bytes, table too large for shared memory)
     Buf slots32;             // 32-byte slots: 3 key words + (first row | run length << 32)
 };
+// Row slots (gather.cu): the output columns of the sorted rows re-laid as one fixed-size slot per row (their
+// bytes back to back) + one packed word of lengths per row, so that a join fetches an index row with ONE random
+// access instead of two per column.  Built lazily per set of output columns when every value is short.
+struct RowSlots {
+    bool usable = false;
+    uint32_t S = 0;   // slot bytes (multiple of 16, <= 64)
+    Buf slots;        // uint8[nrows][S]
+    Buf lens;         // uint32[nrows]: length of column c in bits 8c..8c+7
+};
 struct Index {
     Ctx* ctx = nullptr;
     std::shared_ptr<Table> table;      // sorted rows
@@ -99,6 +108,7 @@ struct Index {
     uint32_t image_words = 0;          // uint64 words per row of the key image
     Buf image;                         // uint64[image_words][nrows] (word-major / SoA)
     std::map<int, HashTable> hash;     // by number of leading key columns (built lazily, under `mu`)
+    std::map<std::vector<int>, RowSlots> row_slots;  // by output column set (built lazily, under `mu`)
     std::mutex mu;                     // several contexts may probe one index concurrently
 };
 
@@ -159,6 +169,8 @@ Column gather_column(Ctx* c, const Column& src, const uint32_t* row_ids, int64_t
 std::shared_ptr<Table> gather_rows(Ctx* c, const Table& t, const uint32_t* row_ids, int64_t nout);
 std::shared_ptr<Table> filter_table(Ctx* c, const Table& t, const cpb_pred* pred);
 Column materialize(Ctx* c, const Column& col, int64_t nrows);  // view -> own compact buffers
+// rows `ids` of the index's sorted table restricted to columns `cols` (row-slot path when it pays, else gather_rows)
+std::shared_ptr<Table> gather_index_rows(Ctx* c, Index& ix, const std::vector<int>& cols, const uint32_t* ids, int64_t nout);
 std::shared_ptr<Table> concat_tables(Ctx* c, const std::vector<const Table*>& parts);
 // sort.cu
 std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std::string>& keys, bool unique,

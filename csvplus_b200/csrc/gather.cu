@@ -18,9 +18,12 @@ constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // tile state word: bits 63:62 status (0 none, 1 aggregate, 2 inclusive), bits 61:0 value
-__global__ void __launch_bounds__(SCAN_THREADS) scan_u32_kernel(const uint32_t* in, uint32_t* out, uint64_t n,
-                                                                unsigned long long* state, uint32_t* ticket,
-                                                                unsigned long long* total) {
+// GATHER: the scanned values are the lengths of the strings picked by `ids` (identity when null) from the offsets
+// array `in` -- the length array of a gather is never materialised.
+template <bool GATHER>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_u32_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ ids,
+                                                                uint32_t* out, uint64_t n, unsigned long long* state,
+                                                                uint32_t* ticket, unsigned long long* total) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ unsigned long long s_prefix;
@@ -35,7 +38,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_u32_kernel(const uint32_t* 
         uint32_t v[SCAN_ITEMS];
         uint32_t sum = 0;
 #pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = base + i < n ? in[base + i] : 0; sum += v[i]; }
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            v[i] = 0;
+            if (base + i < n) {
+                if (GATHER) { const uint32_t r = ids ? ids[base + i] : (uint32_t)(base + i); v[i] = in[r + 1] - in[r]; }
+                else v[i] = in[base + i];
+            }
+            sum += v[i];
+        }
         uint32_t inc = warp_incl_scan(sum);
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
@@ -74,8 +84,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_u32_kernel(const uint32_t* 
 
 __global__ void scan_empty_kernel(uint32_t* out, unsigned long long* total) { out[0] = 0; *total = 0; }
 
-// out may alias in; out has n+1 entries (out[n] = total, truncated to 32 bits); *total_dev holds the 64-bit total
-void exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, uint64_t n, uint64_t* total_dev) {
+// out may alias in; out has n+1 entries (out[n] = total, truncated to 32 bits); *total_dev holds the 64-bit total.
+// gather_off != nullptr: scan the lengths off[ids[i]+1]-off[ids[i]] instead of `in` (ids may be null = identity).
+static void scan_impl(Ctx* c, const uint32_t* in, const uint32_t* gather_off, const uint32_t* ids, uint32_t* out, uint64_t n,
+                      uint64_t* total_dev) {
     if (n == 0) {
         KernelTimer kt(c, "scan_u32", 0);
         scan_empty_kernel<<<1, 1, 0, c->stream>>>(out, (unsigned long long*)total_dev);
@@ -87,20 +99,45 @@ void exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, uint64_t n, u
     unsigned long long* state = st->as<unsigned long long>() + 8;
     uint32_t* ticket = st->as<uint32_t>();
     uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)c->sm_count * 8);
-    KernelTimer kt(c, "scan_u32", n * 8);
-    scan_u32_kernel<<<grid, SCAN_THREADS, 0, c->stream>>>(in, out, n, state, ticket, (unsigned long long*)total_dev);
+    if (gather_off) {
+        KernelTimer kt(c, "scan_gather_len", n * (ids ? 16 : 12));
+        scan_u32_kernel<true><<<grid, SCAN_THREADS, 0, c->stream>>>(gather_off, ids, out, n, state, ticket, (unsigned long long*)total_dev);
+    } else {
+        KernelTimer kt(c, "scan_u32", n * 8);
+        scan_u32_kernel<false><<<grid, SCAN_THREADS, 0, c->stream>>>(in, nullptr, out, n, state, ticket, (unsigned long long*)total_dev);
+    }
     CPB_CUDA(cudaGetLastError());
+}
+void exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, uint64_t n, uint64_t* total_dev) {
+    scan_impl(c, in, nullptr, nullptr, out, n, total_dev);
 }
 
 // ------------------------------------------------------------------ gather by row ids
-__global__ void gather_len_kernel(const uint32_t* __restrict__ off, const uint32_t* __restrict__ ids, uint32_t* out_len, uint64_t n) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { uint32_t r = ids ? ids[i] : (uint32_t)i; out_len[i] = off[r + 1] - off[r]; }
-}
 // One warp gathers 32 consecutive output values.  Their destination bytes are contiguous, so the lanes first
 // copy their (randomly placed) source strings into a per-warp shared-memory stage laid out like the
 // destination, then the warp writes the stage with aligned 16-byte stores: HBM/L2 see full sectors instead of one
 // scattered byte store per lane.  ids==nullptr means identity (compaction of a view).
+// Copies len bytes from an arbitrarily aligned global source with aligned 8-byte loads (two per 8 bytes at most, the
+// second carried over to the next round): the lanes of a warp read unrelated strings, so every load instruction
+// costs 32 L1 wavefronts and a byte-wise loop is wavefront-bound.  Source buffers are allocated in multiples of
+// 512 bytes (DevBuf), so the aligned word holding the last byte is always readable.
+__device__ __forceinline__ void copy_unaligned(uint8_t* q, const uint8_t* sp, uint32_t len) {
+    if (len == 0) return;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 7u), sh = mis * 8;
+    const unsigned long long* wp = reinterpret_cast<const unsigned long long*>(sp - mis);
+    unsigned long long lo = __ldg(wp);
+    for (uint32_t k = 0; k < len; k += 8) {
+        const uint32_t rem = len - k;
+        unsigned long long v = lo >> sh;
+        if (mis + rem > 8) {  // bytes beyond the current word are needed (this round or the next)
+            const unsigned long long hi = __ldg(++wp);
+            if (sh) v |= hi << (64 - sh);
+            lo = hi;
+        }
+#pragma unroll
+        for (uint32_t b = 0; b < 8; b++) if (b < rem) q[k + b] = (uint8_t)(v >> (8 * b));
+    }
+}
 constexpr int GW_WARPS = 8;
 constexpr int GW_STAGE = 2048;  // bytes staged per warp; longer groups take the direct path
 __global__ void __launch_bounds__(GW_WARPS * 32) gather_copy_kernel(const uint32_t* __restrict__ src_off, const uint8_t* __restrict__ src,
@@ -123,8 +160,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gather_copy_kernel(const uint32
         const uint32_t total = dl - d0, sh = d0 & 15u;
         const uint8_t* sp = src + s;
         if (sh + total <= GW_STAGE) {
-            uint8_t* q = stage + sh + (d - d0);
-            for (uint32_t k = 0; k < len; k++) q[k] = sp[k];
+            copy_unaligned(stage + sh + (d - d0), sp, len);
             __syncwarp();
             uint8_t* gb = dst + (d0 - sh);
             for (uint32_t x = lane * 16; x < sh + total; x += 32 * 16) {
@@ -133,8 +169,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gather_copy_kernel(const uint32
             }
             __syncwarp();
         } else {
-            uint8_t* dp = dst + d;
-            for (uint32_t k = 0; k < len; k++) dp[k] = sp[k];
+            copy_unaligned(dst + d, sp, len);
         }
     }
 }
@@ -152,12 +187,7 @@ static std::vector<Column> gather_columns(Ctx* c, const std::vector<const Column
         out[k].name = srcs[k]->name;
         out[k].offsets = dev_alloc(c, ((size_t)nout + 1) * 4);
         uint32_t* o = out[k].offsets->as<uint32_t>();
-        if (nout) {
-            KernelTimer kt(c, "gather_len", (uint64_t)nout * 12);
-            gather_len_kernel<<<blocks_for(nout, 256), 256, 0, c->stream>>>(srcs[k]->off(), ids, o, (uint64_t)nout);
-            CPB_CUDA(cudaGetLastError());
-        }
-        exclusive_scan_u32(c, o, o, (uint64_t)nout, totals->as<uint64_t>() + k);
+        scan_impl(c, nullptr, srcs[k]->off(), ids, o, (uint64_t)nout, totals->as<uint64_t>() + k);
     }
     uint64_t* ht = (uint64_t*)c->pinned_scratch(srcs.size() * 8);
     CPB_CUDA(cudaMemcpyAsync(ht, totals->p, srcs.size() * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -198,6 +228,283 @@ std::shared_ptr<Table> gather_rows(Ctx* c, const Table& t, const uint32_t* row_i
 }
 
 Column materialize(Ctx* c, const Column& col, int64_t nrows) { return gather_columns(c, {&col}, nullptr, nrows)[0]; }
+
+// ------------------------------------------------------------------ row slots: one random access per gathered index row
+// A join reads index rows in probe order, i.e. at random: per output column that is one access to the offsets and
+// one to the bytes, each a 64-byte DRAM granule once the index outgrows L2 (measured: 9 GB of DRAM reads to gather
+// 0.7 GB).  Short rows are therefore re-laid once per index as fixed-size slots (all output columns back to back) +
+// one packed word of lengths; a gather then costs one L2-friendly 4-byte read (lengths -> offsets of all columns in
+// one scan) and one slot read (bytes of all columns in one pass).
+constexpr int RS_MAXC = 4;       // columns per slot set (lengths are 8 bits each in one word)
+constexpr uint32_t RS_MAXS = 64; // bytes per slot
+struct SlotCols { int nc; const uint32_t* off[RS_MAXC]; const uint8_t* data[RS_MAXC]; };
+struct SlotOut { uint32_t* off[RS_MAXC]; uint8_t* data[RS_MAXC]; };
+
+__global__ void slot_lens_kernel(SlotCols sc, uint64_t n, uint32_t* lens, uint32_t* stat) {  // stat: [0] max row bytes, [1] a value > 255 bytes
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t tot = 0, packed = 0, bad = 0;
+    if (r < n) {
+        for (int c = 0; c < sc.nc; c++) {
+            const uint32_t l = sc.off[c][r + 1] - sc.off[c][r];
+            bad |= l > 255u;
+            packed |= (l & 255u) << (8 * c);
+            tot += l;
+        }
+        lens[r] = packed;
+    }
+    tot = __reduce_max_sync(0xffffffffu, tot);
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) { atomicMax(&stat[0], tot); if (bad) stat[1] = 1u; }
+}
+__global__ void slot_fill_kernel(SlotCols sc, uint64_t n, uint32_t S, uint8_t* slots) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint8_t* q = slots + r * S;
+    uint32_t pos = 0;
+    for (int c = 0; c < sc.nc; c++) {
+        const uint32_t s = sc.off[c][r], l = sc.off[c][r + 1] - s;
+        const uint8_t* p = sc.data[c] + s;
+        for (uint32_t k = 0; k < l; k++) q[pos + k] = p[k];
+        pos += l;
+    }
+    for (; pos < S; pos++) q[pos] = 0;
+}
+
+// exclusive scans of the NC length fields of lens[ids[i]] in one pass (same chained look-back as scan_u32_kernel;
+// warp c resolves column c)
+constexpr int LS_ITEMS = 8;
+constexpr int LS_TILE = SCAN_THREADS * LS_ITEMS;
+template <int NC>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lens_kernel(const uint32_t* __restrict__ lens, const uint32_t* __restrict__ ids, uint64_t n,
+                                                                 SlotOut out, unsigned long long* state, uint32_t* ticket,
+                                                                 unsigned long long* totals) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[NC][SCAN_THREADS / 32];
+    __shared__ unsigned long long s_prefix[NC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t ntiles = (n + LS_TILE - 1) / LS_TILE;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint64_t tile = s_tile;
+        if (tile >= ntiles) break;
+        const uint64_t base = tile * LS_TILE + (uint64_t)tid * LS_ITEMS;
+        uint32_t p[LS_ITEMS];
+        if (base + LS_ITEMS <= n) {
+            const uint4 a = *reinterpret_cast<const uint4*>(ids + base), b = *reinterpret_cast<const uint4*>(ids + base + 4);
+            p[0] = lens[a.x]; p[1] = lens[a.y]; p[2] = lens[a.z]; p[3] = lens[a.w];
+            p[4] = lens[b.x]; p[5] = lens[b.y]; p[6] = lens[b.z]; p[7] = lens[b.w];
+        } else {
+#pragma unroll
+            for (int i = 0; i < LS_ITEMS; i++) p[i] = base + i < n ? lens[ids[base + i]] : 0u;
+        }
+        uint32_t sum[NC], inc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            sum[c] = 0;
+#pragma unroll
+            for (int i = 0; i < LS_ITEMS; i++) sum[c] += (p[i] >> (8 * c)) & 255u;
+            inc[c] = warp_incl_scan(sum[c]);
+            if (lane == 31) s_warp[c][warp] = inc[c];
+        }
+        __syncthreads();
+        if (warp < NC) {
+            const int c = warp;
+            uint32_t tot = 0;
+#pragma unroll
+            for (int i = 0; i < SCAN_THREADS / 32; i++) tot += s_warp[c][i];
+            unsigned long long* st = state + c;  // state[tile * NC + c]
+            unsigned long long excl = 0;
+            if (tile == 0) {
+                if (lane == 0) atomicExch(&st[0], (2ull << 62) | tot);
+            } else {
+                if (lane == 0) atomicExch(&st[tile * NC], (1ull << 62) | tot);
+                int64_t b = (int64_t)tile - 1;
+                for (;;) {
+                    const int64_t q = b - lane;
+                    unsigned long long sv = 2ull << 62;
+                    if (q >= 0) { do { sv = ld_relaxed_u64((const uint64_t*)&st[q * NC]); } while ((sv >> 62) == 0); }
+                    const uint32_t incl = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                    const int f = __ffs(incl) - 1;
+                    const unsigned long long val = (f < 0 || lane <= f) ? (sv & ((1ull << 62) - 1)) : 0ull;
+                    excl += warp_sum_u64(val);
+                    if (f >= 0) break;
+                    b -= 32;
+                }
+                if (lane == 0) atomicExch(&st[tile * NC], (2ull << 62) | (excl + tot));
+            }
+            if (lane == 0) {
+                s_prefix[c] = excl;
+                if (tile == ntiles - 1) { totals[c] = excl + tot; out.off[c][n] = (uint32_t)(excl + tot); }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            uint32_t run = (uint32_t)s_prefix[c] + (inc[c] - sum[c]);
+#pragma unroll
+            for (int i = 0; i < SCAN_THREADS / 32; i++) if (i < warp) run += s_warp[c][i];
+            uint32_t* o = out.off[c];
+            if (base + LS_ITEMS <= n) {
+                uint32_t v[LS_ITEMS];
+#pragma unroll
+                for (int i = 0; i < LS_ITEMS; i++) { v[i] = run; run += (p[i] >> (8 * c)) & 255u; }
+                *reinterpret_cast<uint4*>(o + base) = make_uint4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<uint4*>(o + base + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < LS_ITEMS; i++) { if (base + i < n) o[base + i] = run; run += (p[i] >> (8 * c)) & 255u; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// One warp gathers 32 consecutive output rows: every lane pulls its row's slot into shared memory with 16-byte
+// loads (the one random access), then, column by column, the warp lays the values out like the destination in the
+// staging buffer and writes it with aligned 16-byte stores (as gather_copy_kernel does).
+template <int NC>
+__global__ void __launch_bounds__(GW_WARPS * 32) slot_copy_kernel(const uint8_t* __restrict__ slots, uint32_t S, const uint32_t* __restrict__ ids,
+                                                                  SlotOut out, uint64_t n) {
+    __shared__ __align__(16) uint8_t slot_sm[GW_WARPS][32 * RS_MAXS];
+    __shared__ __align__(16) uint8_t stage_all[GW_WARPS][GW_STAGE + 16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* stage = stage_all[warp];
+    uint8_t* myslot = slot_sm[warp] + lane * S;
+    const uint64_t nwarps = (uint64_t)gridDim.x * GW_WARPS;
+    for (uint64_t g = (uint64_t)blockIdx.x * GW_WARPS + warp; g * 32 < n; g += nwarps) {
+        const uint64_t i = g * 32 + lane;
+        const bool valid = i < n;
+        if (valid) {
+            const uint4* sp = reinterpret_cast<const uint4*>(slots + (uint64_t)ids[i] * S);
+            for (uint32_t j = 0; j < S / 16; j++) reinterpret_cast<uint4*>(myslot)[j] = __ldg(sp + j);
+        }
+        const uint64_t last = (g * 32 + 31 < n ? g * 32 + 31 : n - 1) - g * 32;
+        uint32_t pos = 0;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            uint32_t d = 0, len = 0;
+            if (valid) { d = out.off[c][i]; len = out.off[c][i + 1] - d; }
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+            const uint32_t dl = __shfl_sync(0xffffffffu, d + len, (int)last);
+            const uint32_t total = dl - d0, sh = d0 & 15u;
+            const uint8_t* sp = myslot + pos;
+            uint8_t* dst = out.data[c];
+            if (sh + total <= GW_STAGE) {
+                uint8_t* q = stage + sh + (d - d0);
+                for (uint32_t k = 0; k < len; k++) q[k] = sp[k];
+                __syncwarp();
+                uint8_t* gb = dst + (d0 - sh);
+                for (uint32_t x = lane * 16; x < sh + total; x += 32 * 16) {
+                    if (x >= sh && x + 16 <= sh + total) *reinterpret_cast<uint4*>(gb + x) = *reinterpret_cast<const uint4*>(stage + x);
+                    else for (uint32_t y = x; y < x + 16; y++) if (y >= sh && y < sh + total) gb[y] = stage[y];
+                }
+                __syncwarp();
+            } else {
+                uint8_t* dp = dst + d;
+                for (uint32_t k = 0; k < len; k++) dp[k] = sp[k];
+            }
+            pos += len;
+        }
+        __syncwarp();  // the slots are overwritten by the next round
+    }
+}
+
+static RowSlots& ensure_row_slots(Ctx* c, Index& ix, const std::vector<int>& cols) {
+    std::lock_guard<std::mutex> lk(ix.mu);
+    auto it = ix.row_slots.find(cols);
+    if (it != ix.row_slots.end()) return it->second;
+    RowSlots rs;
+    const Table& t = *ix.table;
+    const uint64_t n = (uint64_t)t.nrows;
+    if (n > 0 && !cols.empty() && cols.size() <= (size_t)RS_MAXC) {
+        SlotCols sc{};
+        sc.nc = (int)cols.size();
+        for (int k = 0; k < sc.nc; k++) { sc.off[k] = t.cols[cols[k]].off(); sc.data[k] = t.cols[cols[k]].bytes(); }
+        Buf lens = dev_alloc(c, n * 4), stat = dev_alloc(c, 8);
+        CPB_CUDA(cudaMemsetAsync(stat->p, 0, 8, c->stream));
+        uint64_t col_bytes = n * 4 * sc.nc;
+        {
+            KernelTimer kt(c, "slot_build", col_bytes + n * 4);
+            slot_lens_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sc, n, lens->as<uint32_t>(), stat->as<uint32_t>());
+            CPB_CUDA(cudaGetLastError());
+        }
+        uint32_t* hs = (uint32_t*)c->pinned_scratch(8);
+        CPB_CUDA(cudaMemcpyAsync(hs, stat->p, 8, cudaMemcpyDeviceToHost, c->stream));
+        CPB_CUDA(cudaStreamSynchronize(c->stream));
+        if (hs[1] == 0 && hs[0] <= RS_MAXS) {
+            rs.S = std::max<uint32_t>(16, (hs[0] + 15) & ~15u);
+            rs.slots = dev_alloc(c, n * rs.S);
+            rs.lens = lens;
+            KernelTimer kt(c, "slot_build", n * rs.S * 2);
+            slot_fill_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sc, n, rs.S, rs.slots->as<uint8_t>());
+            CPB_CUDA(cudaGetLastError());
+            rs.usable = true;
+        }
+    }
+    CPB_CUDA(cudaStreamSynchronize(c->stream));  // complete before another context (stream) can find it in the map
+    return ix.row_slots.emplace(cols, std::move(rs)).first->second;
+}
+
+std::shared_ptr<Table> gather_index_rows(Ctx* c, Index& ix, const std::vector<int>& cols, const uint32_t* ids, int64_t nout) {
+    const Table& t = *ix.table;
+    Table sub; sub.ctx = c; sub.nrows = t.nrows; sub.first_line = t.first_line;
+    for (int ci : cols) sub.cols.push_back(t.cols[ci]);
+    static const bool disabled = getenv("CPB_NO_ROWSLOTS") != nullptr;
+    bool use = !disabled && ids != nullptr && nout > 0 && !cols.empty() && cols.size() <= (size_t)RS_MAXC;
+    if (use) {
+        bool built;
+        { std::lock_guard<std::mutex> lk(ix.mu); built = ix.row_slots.count(cols) != 0; }
+        if (!built && nout < t.nrows) use = false;  // laying the slots out costs about one gather of the whole index
+    }
+    if (!use) return gather_rows(c, sub, ids, nout);
+    RowSlots& rs = ensure_row_slots(c, ix, cols);
+    if (!rs.usable) return gather_rows(c, sub, ids, nout);
+
+    const int nc = (int)cols.size();
+    auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = nout; r->first_line = t.first_line;
+    SlotOut so{};
+    std::vector<Column> out(nc);
+    for (int k = 0; k < nc; k++) {
+        out[k].name = t.cols[cols[k]].name;
+        out[k].offsets = dev_alloc(c, ((size_t)nout + 1) * 4);
+        so.off[k] = out[k].offsets->as<uint32_t>();
+    }
+    const uint64_t n = (uint64_t)nout, ntiles = (n + LS_TILE - 1) / LS_TILE;
+    Buf st = dev_alloc(c, ntiles * nc * 8 + 64 + RS_MAXC * 8);
+    CPB_CUDA(cudaMemsetAsync(st->p, 0, ntiles * nc * 8 + 64 + RS_MAXC * 8, c->stream));
+    uint32_t* ticket = st->as<uint32_t>();
+    unsigned long long* totals = st->as<unsigned long long>() + 1;
+    unsigned long long* state = st->as<unsigned long long>() + 8 + RS_MAXC;
+    {
+        KernelTimer kt(c, "slot_scan_lens", n * (8 + 4 * (uint64_t)nc));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)c->sm_count * 8);
+#define CPB_LS(NC) scan_lens_kernel<NC><<<grid, SCAN_THREADS, 0, c->stream>>>(rs.lens->as<uint32_t>(), ids, n, so, state, ticket, totals)
+        switch (nc) { case 1: CPB_LS(1); break; case 2: CPB_LS(2); break; case 3: CPB_LS(3); break; default: CPB_LS(4); break; }
+#undef CPB_LS
+        CPB_CUDA(cudaGetLastError());
+    }
+    uint64_t* ht = (uint64_t*)c->pinned_scratch(RS_MAXC * 8);
+    CPB_CUDA(cudaMemcpyAsync(ht, totals, nc * 8, cudaMemcpyDeviceToHost, c->stream));
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    uint64_t all = 0;
+    for (int k = 0; k < nc; k++) {
+        if (ht[k] > 0xffffffffull) throw DataError{CPB_E_TOO_LARGE, k, 0, false, "a result column exceeds 4 GiB; process in smaller batches"};
+        out[k].data = dev_alloc(c, ht[k] + 16);
+        so.data[k] = out[k].data->as<uint8_t>();
+        all += ht[k];
+    }
+    {
+        KernelTimer kt(c, "slot_copy", 2 * all + n * (4 + 4 * (uint64_t)nc));
+        const uint32_t gblocks = (uint32_t)std::min<uint64_t>((n + GW_WARPS * 32 - 1) / (GW_WARPS * 32), (uint64_t)c->sm_count * 16);
+#define CPB_SC(NC) slot_copy_kernel<NC><<<gblocks, GW_WARPS * 32, 0, c->stream>>>(rs.slots->as<uint8_t>(), rs.S, ids, so, n)
+        switch (nc) { case 1: CPB_SC(1); break; case 2: CPB_SC(2); break; case 3: CPB_SC(3); break; default: CPB_SC(4); break; }
+#undef CPB_SC
+        CPB_CUDA(cudaGetLastError());
+    }
+    for (int k = 0; k < nc; k++) r->cols.push_back(out[k]);
+    return r;
+}
 
 // ------------------------------------------------------------------ Filter over a table
 struct FilterCols { const uint32_t* off[MAXTERMS]; const uint8_t* data[MAXTERMS]; };

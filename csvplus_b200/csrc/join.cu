@@ -236,7 +236,9 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
     }
     // output schema: mergeRows(indexRow, probeRow) — probe wins name collisions (csvplus.go:571-583)
     std::vector<const Column*> icols, pcols;
-    if (!anti) for (auto& col : ix.table->cols) if (probe.find(col.name) < 0) icols.push_back(&col);
+    std::vector<int> icol_idx;
+    if (!anti) for (size_t q = 0; q < ix.table->cols.size(); q++)
+        if (probe.find(ix.table->cols[q].name) < 0) { icols.push_back(&ix.table->cols[q]); icol_idx.push_back((int)q); }
     for (auto& col : probe.cols) pcols.push_back(&col);
 
     auto out = std::make_shared<Table>(); out->ctx = c; out->first_line = probe.first_line;
@@ -308,9 +310,7 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
     if (m > 0xfffffffeull) throw DataError{CPB_E_TOO_LARGE, -1, 0, false, "join result exceeds 2^32-2 rows; probe in smaller batches"};
     if (m == 0) return empty_result();
     if (probe_identity) {
-        Table it; it.ctx = c; it.nrows = (int64_t)ni;
-        for (auto* p : icols) it.cols.push_back(*p);
-        auto gi = gather_rows(c, it, lo->as<uint32_t>(), (int64_t)m);  // lo[i] is the single matching index row
+        auto gi = gather_index_rows(c, ix, icol_idx, lo->as<uint32_t>(), (int64_t)m);  // lo[i] is the single matching index row
         out->nrows = (int64_t)m;
         for (auto& col : gi->cols) out->cols.push_back(col);
         for (auto* p : pcols) out->cols.push_back(*p);
@@ -323,11 +323,9 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
                                                                   iid->as<uint32_t>(), np);
         CPB_CUDA(cudaGetLastError());
     }
-    Table it; it.ctx = c; it.nrows = (int64_t)ni;
-    for (auto* p : icols) it.cols.push_back(*p);
     Table pt; pt.ctx = c; pt.nrows = (int64_t)np;
     for (auto* p : pcols) pt.cols.push_back(*p);
-    auto gi = gather_rows(c, it, iid->as<uint32_t>(), (int64_t)m);
+    auto gi = gather_index_rows(c, ix, icol_idx, iid->as<uint32_t>(), (int64_t)m);
     auto gp = gather_rows(c, pt, pid->as<uint32_t>(), (int64_t)m);
     out->nrows = (int64_t)m;
     for (auto& col : gi->cols) out->cols.push_back(col);

@@ -419,7 +419,7 @@ void index_dedup_apply(Ctx* c, Index& ix, const std::vector<int64_t>& keep, bool
         gather_u64_kernel<<<nblk(m, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>() + (uint64_t)w * n, ids->as<uint32_t>(),
                                                                simg->as<uint64_t>() + (uint64_t)w * m, m);
     CPB_CUDA(cudaGetLastError());
-    ix.table = nt; ix.image = simg; ix.hash.clear();
+    ix.table = nt; ix.image = simg; ix.hash.clear(); ix.row_slots.clear();
 }
 
 }  // namespace cpb

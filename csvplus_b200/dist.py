@@ -31,6 +31,42 @@ def allgather_ragged(t, dist, group=None):
     return [out[r * mx: r * mx + sizes[r]] for r in range(world)]
 
 
+def pack_layout(seg_bytes, align: int = 16):
+    """byte offset of every segment in a packed buffer (each segment starts `align`-aligned) and the total size"""
+    offs, pos = [], 0
+    for b in seg_bytes:
+        offs.append(pos)
+        pos += (int(b) + align - 1) // align * align
+    return offs, pos
+
+
+def allgather_packed(segments, dist, group=None):
+    """all-gather-v of SEVERAL ragged uint8 tensors with one size exchange and one data collective.
+
+    Every rank passes the same number (>= 1) of 1-D uint8 tensors; segment k of rank r may have any length.  The
+    segments are packed 16-byte aligned into one buffer, padded to the longest rank, and gathered with a single
+    all_gather_into_tensor.  Returns out[r][k] = view of rank r's segment k (rank order).
+    """
+    import torch
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    k = len(segments)
+    dev = segments[0].device
+    meta = torch.tensor([s.numel() for s in segments], dtype=torch.int64, device=dev)
+    allmeta = torch.empty(world * k, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allmeta, meta, group=group)
+    sizes = allmeta.view(world, k).tolist()  # the one host sync of the exchange
+    layouts = [pack_layout(sizes[r]) for r in range(world)]
+    mx = max(max(tot for _, tot in layouts), 16)
+    pack = torch.empty(mx, dtype=torch.uint8, device=dev)
+    for s, o in zip(segments, layouts[rank][0]):
+        if s.numel():
+            pack[o: o + s.numel()].copy_(s)
+    out = torch.empty(world * mx, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, pack, group=group)
+    return [[out[r * mx + o: r * mx + o + sizes[r][j]] for j, o in enumerate(layouts[r][0])] for r in range(world)]
+
+
 class _DevArr:
     def __init__(self, ptr: int, nbytes: int):
         self.__cuda_array_interface__ = {"shape": (max(nbytes, 1),), "typestr": "|u1", "data": (ptr, False), "version": 2}
@@ -50,21 +86,23 @@ def allgather_table(ctx, table, dist, group=None):
     cols = table.columns
     n = len(table)
     ctx.sync()
-    parts_off, parts_data = [], []
+    segs = []
     nb = C.c_uint64()
     for i, c in enumerate(cols):
         po, pd = table.device_column(c)
         ctx.lib.cpb_table_col_bytes(ctx.h, table.h, i, 0, n, C.byref(nb))
-        parts_off.append(allgather_ragged(_as_tensor(po, 4 * (n + 1)), dist, group))
-        parts_data.append(allgather_ragged(_as_tensor(pd, nb.value), dist, group))
+        segs.append(_as_tensor(po, 4 * (n + 1)))
+        segs.append(_as_tensor(pd, nb.value))
+    parts = allgather_packed(segs, dist, group)  # one size exchange + one collective for all columns
     torch.cuda.synchronize()
     world = dist.get_world_size(group)
     names, keep = _strs(cols)
     tabs = []
     for r in range(world):
-        rows = parts_off[0][r].numel() // 4 - 1
-        oa = (C.c_void_p * len(cols))(*[parts_off[k][r].data_ptr() for k in range(len(cols))])
-        da = (C.c_void_p * len(cols))(*[parts_data[k][r].data_ptr() if parts_data[k][r].numel() else 0 for k in range(len(cols))])
+        rows = parts[r][0].numel() // 4 - 1
+        oa = (C.c_void_p * len(cols))(*[parts[r][2 * k].data_ptr() for k in range(len(cols))])
+        da = (C.c_void_p * len(cols))(*[parts[r][2 * k + 1].data_ptr() if parts[r][2 * k + 1].numel() else 0
+                                        for k in range(len(cols))])
         h = C.c_void_p()
         st = ctx.lib.cpb_table_from_device(ctx.h, len(cols), names, oa, da, rows, C.byref(h))
         if st:

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from csvplus_b200.dist import allgather_ragged, shard_range
+from csvplus_b200.dist import allgather_packed, allgather_ragged, pack_layout, shard_range
 
 
 def _free_port():
@@ -28,8 +28,11 @@ def _worker(rank, world, port, q):
         po = allgather_ragged(torch.from_numpy(off.view(np.uint8).copy()), dist)
         pd = allgather_ragged(torch.from_numpy(data.copy()), dist)
         empty = allgather_ragged(torch.zeros(0 if rank == 0 else 5, dtype=torch.uint8), dist)
+        # the same column + an empty/ragged segment through the packed (single-collective) gather
+        pk = allgather_packed([torch.from_numpy(off.view(np.uint8).copy()), torch.from_numpy(data.copy()),
+                               torch.zeros(0 if rank == 0 else 5, dtype=torch.uint8)], dist)
         q.put((rank, [p.numpy().tobytes() for p in po], [p.numpy().tobytes() for p in pd], [e.numel() for e in empty],
-               off.tobytes(), data.tobytes()))
+               off.tobytes(), data.tobytes(), [[s.numpy().tobytes() for s in r] for r in pk]))
     finally:
         dist.destroy_process_group()
 
@@ -47,9 +50,17 @@ def test_allgather_ragged_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     offs = [r[4] for r in res]; datas = [r[5] for r in res]
-    for rank, po, pd, empty, _, _ in res:
+    for rank, po, pd, empty, _, _, pk in res:
         assert po == offs and pd == datas  # every rank sees every rank's columns, in rank order
         assert empty == [0, 5]
+        assert [r[0] for r in pk] == offs and [r[1] for r in pk] == datas
+        assert [len(r[2]) for r in pk] == [0, 5]
+
+
+def test_pack_layout_alignment():
+    offs, tot = pack_layout([0, 1, 16, 17, 0, 5])
+    assert offs == [0, 0, 16, 32, 64, 64] and tot == 80
+    assert pack_layout([]) == ([], 0)
 
 
 def test_shard_range_partitions_rows():

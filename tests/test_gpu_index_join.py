@@ -291,3 +291,51 @@ def test_long_chain():
         assert sorted(row) == ["name", "price", "product", "qty", "surname"]
     assert len(cp.Take(orders).ToRows()) == 10000
     assert len(cp.Take(products).ToRows()) == 8
+
+
+def _kv_csv(header, rows):
+    return (",".join(header) + "\n" + "".join(",".join(r) + "\n" for r in rows)).encode()
+
+
+@pytest.mark.parametrize("shape", ["slots4", "slots1_empty", "too_wide", "too_long_value", "five_cols"])
+def test_join_row_slot_path_and_fallbacks(shape):
+    """gather of index rows: fixed-size row slots (<= 4 output columns, values <= 255 bytes, row <= 64 bytes) and
+    the per-column fallback must both reproduce mergeRows (csvplus.go:571-583) exactly"""
+    import csvplus_b200 as cp
+    rng = random.Random(sum(shape.encode()))
+    nidx, nprobe = 257, 1999
+
+    def word(maxlen):
+        return "".join(rng.choice("abcxyz01") for _ in range(rng.randrange(0, maxlen + 1)))
+    if shape == "slots4":
+        hdr = ["k", "a", "b", "c"]; mk = lambda i: [str(i), word(20), word(20), word(18)]
+    elif shape == "slots1_empty":
+        hdr = ["k"]; mk = lambda i: [str(i)]
+    elif shape == "too_wide":
+        hdr = ["k", "a", "b"]; mk = lambda i: [str(i), word(40), word(40)]
+    elif shape == "too_long_value":
+        hdr = ["k", "a"]; mk = lambda i: [str(i), "q" * 300 if i == 77 else word(5)]
+    else:
+        hdr = ["k", "a", "b", "c", "d"]; mk = lambda i: [str(i), word(3), word(3), word(3), word(3)]
+    # non-unique index: every third key appears twice
+    irows = [mk(i) for i in range(nidx)] + [mk(i) for i in range(0, nidx, 3)]
+    rng.shuffle(irows)
+    idata = _kv_csv(hdr, irows)
+    pdata = _kv_csv(["pid", "k2"], [[str(j), str(rng.randrange(nidx + 20))] for j in range(nprobe)])
+    idx = cp.Take(cp.FromBytes(idata)).IndexOn("k")
+    oidx = orc.reader_rows(idata).index_on("k")
+    tp, _ = cp.Take(cp.FromBytes(pdata))._table()
+    op = orc.reader_rows(pdata)
+    oj = op.join(oidx, "k2")
+    assert len(oj) > nprobe
+    assert_table_equals_oracle(tp.join(idx, "k2"), oj)
+    # second probe of the same index with fewer rows than the index (cached slots are reused)
+    small = _kv_csv(["pid", "k2"], [[str(j), str(j * 7 % nidx)] for j in range(33)])
+    ts, _ = cp.Take(cp.FromBytes(small))._table()
+    assert_table_equals_oracle(ts.join(idx, "k2"), orc.reader_rows(small).join(oidx, "k2"))
+    # unique index: identity fast path (every probe row matches exactly once)
+    udata = _kv_csv(hdr, [mk(i) for i in range(nidx)])
+    uidx = cp.Take(cp.FromBytes(udata)).UniqueIndexOn("k")
+    exact = _kv_csv(["pid", "k2"], [[str(j), str(rng.randrange(nidx))] for j in range(nprobe)])
+    te, _ = cp.Take(cp.FromBytes(exact))._table()
+    assert_table_equals_oracle(te.join(uidx, "k2"), orc.reader_rows(exact).join(orc.reader_rows(udata).unique_index_on("k"), "k2"))

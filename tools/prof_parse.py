@@ -21,7 +21,7 @@ else:
     ncust = rows // 10
     cust = ctx.gen_csv("customers", (0, ncust), n_cust=ncust, permute=True)
     orders = ctx.gen_csv("orders", (0, rows), n_cust=ncust, n_prod=1000)
-    for _ in range(2):
+    for _ in range(int(os.environ.get("PROF_ITERS", "2"))):
         tc, _ = cp.parse_csv(ctx, cust, spec=[("id", -1), ("name", -1), ("surname", -1)])
         idx = tc.index_on("id", unique=True)
         to, _ = cp.parse_csv(ctx, orders, spec=[("cust_id", -1), ("prod_id", -1), ("qty", -1), ("ts", -1)])
