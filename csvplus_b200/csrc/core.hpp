@@ -89,6 +89,8 @@ struct HashTable {
     Buf heads;               // uint32[nheads+1]: sorted position of each distinct prefix; heads[nheads] = nrows
     uint64_t nslots32 = 0;   // embedded-key table (prefix <= 24 bytes, table too large for shared memory)
     Buf slots32;             // 32-byte slots: 3 key words + (first row | run length << 32)
+    uint64_t nslots16 = 0;   // unique keys with prefix <= 12 bytes: 16-byte slots (12 key bytes + row + 1)
+    Buf slots16;
 };
 // Row slots (gather.cu): the output columns of the sorted rows re-laid as one fixed-size slot per row (their
 // bytes back to back) + one packed word of lengths per row, so that a join fetches an index row with ONE random

@@ -256,18 +256,27 @@ __global__ void slot_lens_kernel(SlotCols sc, uint64_t n, uint32_t* lens, uint32
     bad = __any_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0) { atomicMax(&stat[0], tot); if (bad) stat[1] = 1u; }
 }
-__global__ void slot_fill_kernel(SlotCols sc, uint64_t n, uint32_t S, uint8_t* slots) {
-    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    uint8_t* q = slots + r * S;
-    uint32_t pos = 0;
-    for (int c = 0; c < sc.nc; c++) {
-        const uint32_t s = sc.off[c][r], l = sc.off[c][r + 1] - s;
-        const uint8_t* p = sc.data[c] + s;
-        for (uint32_t k = 0; k < l; k++) q[pos + k] = p[k];
-        pos += l;
+// one block lays out 256 consecutive slots in shared memory (row stride padded to an odd number of words: no bank
+// conflicts) and writes them with coalesced 16-byte stores
+constexpr uint32_t RS_PAD = 4;
+__global__ void __launch_bounds__(256) slot_fill_kernel(SlotCols sc, uint64_t n, uint32_t S, uint8_t* slots) {
+    __shared__ __align__(16) uint8_t sm[256 * (RS_MAXS + RS_PAD)];
+    const uint64_t r0 = (uint64_t)blockIdx.x * 256, r = r0 + threadIdx.x;
+    uint8_t* q = sm + threadIdx.x * (S + RS_PAD);
+    if (r < n) {
+        uint32_t pos = 0;
+        for (int c = 0; c < sc.nc; c++) {
+            const uint32_t s = sc.off[c][r], l = sc.off[c][r + 1] - s;
+            copy_unaligned(q + pos, sc.data[c] + s, l);
+            pos += l;
+        }
+        for (; pos < S; pos++) q[pos] = 0;
     }
-    for (; pos < S; pos++) q[pos] = 0;
+    __syncthreads();
+    const uint32_t rows = (uint32_t)(n - r0 < 256 ? n - r0 : 256), wps = S / 4;  // words per slot
+    uint32_t* g = reinterpret_cast<uint32_t*>(slots + r0 * S);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sm);
+    for (uint32_t x = threadIdx.x; x < rows * wps; x += 256) g[x] = sw[(x / wps) * (wps + RS_PAD / 4) + x % wps];
 }
 
 // exclusive scans of the NC length fields of lens[ids[i]] in one pass (same chained look-back as scan_u32_kernel;
@@ -366,18 +375,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lens_kernel(const uint32_t*
 template <int NC>
 __global__ void __launch_bounds__(GW_WARPS * 32) slot_copy_kernel(const uint8_t* __restrict__ slots, uint32_t S, const uint32_t* __restrict__ ids,
                                                                   SlotOut out, uint64_t n) {
-    __shared__ __align__(16) uint8_t slot_sm[GW_WARPS][32 * RS_MAXS];
+    __shared__ __align__(16) uint8_t slot_sm[GW_WARPS][32 * (RS_MAXS + RS_PAD)];
     __shared__ __align__(16) uint8_t stage_all[GW_WARPS][GW_STAGE + 16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* stage = stage_all[warp];
-    uint8_t* myslot = slot_sm[warp] + lane * S;
+    uint8_t* myslot = slot_sm[warp] + lane * (S + RS_PAD);  // odd word stride: conflict-free byte reads
     const uint64_t nwarps = (uint64_t)gridDim.x * GW_WARPS;
     for (uint64_t g = (uint64_t)blockIdx.x * GW_WARPS + warp; g * 32 < n; g += nwarps) {
         const uint64_t i = g * 32 + lane;
         const bool valid = i < n;
         if (valid) {
             const uint4* sp = reinterpret_cast<const uint4*>(slots + (uint64_t)ids[i] * S);
-            for (uint32_t j = 0; j < S / 16; j++) reinterpret_cast<uint4*>(myslot)[j] = __ldg(sp + j);
+            for (uint32_t j = 0; j < S / 16; j++) {
+                const uint4 v = __ldg(sp + j);
+                uint32_t* w = reinterpret_cast<uint32_t*>(myslot) + 4 * j;
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            }
         }
         const uint64_t last = (g * 32 + 31 < n ? g * 32 + 31 : n - 1) - g * 32;
         uint32_t pos = 0;

@@ -123,6 +123,23 @@ __global__ void hash32_insert_kernel(const uint64_t* __restrict__ image, uint64_
     }
 }
 
+__device__ __forceinline__ unsigned long long bswap64(unsigned long long x) {
+    return ((unsigned long long)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | __byte_perm((uint32_t)(x >> 32), 0, 0x0123);
+}
+// the first min(len,16) bytes of a string, little-endian in (a, b), the rest zero: aligned 8-byte loads only (the
+// probe rows of a warp are ~one sector apart, a byte loop costs one L1 request per byte)
+__device__ __forceinline__ void load16(const uint8_t* p, uint32_t len, unsigned long long& a, unsigned long long& b) {
+    a = b = 0;
+    if (len == 0) return;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u), sh = mis * 8;
+    const unsigned long long* wp = reinterpret_cast<const unsigned long long*>(p - mis);
+    const uint32_t need = mis + (len < 16u ? len : 16u);
+    const unsigned long long w0 = __ldg(wp), w1 = need > 8 ? __ldg(wp + 1) : 0ull, w2 = need > 16 ? __ldg(wp + 2) : 0ull;
+    a = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+    b = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+    if (len < 8) { a &= (1ull << (8 * len)) - 1; b = 0; }
+    else if (len < 16) b &= (1ull << (8 * (len - 8))) - 1;
+}
 // packs the probe key exactly like key_pack_kernel (sort.cu), but into three registers
 __device__ __forceinline__ void pack3(const KeyDesc& kd, uint64_t r, unsigned long long& w0, unsigned long long& w1, unsigned long long& w2) {
     unsigned long long cur = 0; int cnt = 0, word = 0;
@@ -132,9 +149,14 @@ __device__ __forceinline__ void pack3(const KeyDesc& kd, uint64_t r, unsigned lo
     for (int k = 0; k < kd.nkeys; k++) {
         const uint32_t s = kd.off[k][r], len = kd.off[k][r + 1] - s, wd = kd.width[k];
         const uint8_t* p = kd.data[k] + s;
-        for (uint32_t i = 0; i < wd; i++) push(i < len ? p[i] : 0u);
+        unsigned long long a, b;
+        load16(p, len < wd ? len : wd, a, b);
+        uint32_t i = 0;
+        if (cnt == 0 && wd >= 8) { flush(bswap64(a)); i = 8; if (wd >= 16) { flush(bswap64(b)); i = 16; } }
+        for (; i < wd; i++)
+            push(i < 8 ? (uint32_t)(a >> (8 * i)) & 255u : i < 16 ? (uint32_t)(b >> (8 * (i - 8))) & 255u : (i < len ? p[i] : 0u));
         const uint32_t lf = len > wd ? 0xffffffffu : len;
-        for (int i = (int)kd.lenbytes[k] - 1; i >= 0; i--) push((lf >> (8 * i)) & 0xffu);
+        for (int i2 = (int)kd.lenbytes[k] - 1; i2 >= 0; i2--) push((lf >> (8 * i2)) & 0xffu);
     }
     if (cnt) flush(cur << (8 * (8 - cnt)));
 }
@@ -149,6 +171,41 @@ __global__ void __launch_bounds__(256) join_probe32_kernel(KeyDesc kd, uint64_t 
             const ulonglong4 sl = *reinterpret_cast<const ulonglong4*>(&slots[s]);  // one 32-byte sector
             if (sl.w == 0ull) break;
             if (sl.x == w0 && sl.y == w1 && sl.z == w2) { l = (uint32_t)sl.w; c = (uint32_t)(sl.w >> 32); break; }
+            if (++s == nslots) s = 0;
+        }
+        lo[i] = l; cnt[i] = c;
+        if (c != 1) *not_one = 1u;  // benign race: every writer stores 1
+    }
+}
+
+// 16-byte slots for key prefixes <= 12 bytes whose runs all have length 1 (unique keys): four slots per 64-byte
+// DRAM granule at load factor 1/2, so a probe costs about one granule (a 32-byte slot at 2/3 costs about two).
+struct __align__(16) Slot16 { unsigned long long k0; uint32_t k1; uint32_t row1; };  // row1 = sorted row + 1; 0 = empty
+__global__ void hash16_insert_kernel(const uint64_t* __restrict__ image, uint64_t n, uint32_t pbytes, const uint32_t* __restrict__ heads,
+                                     uint64_t nheads, Slot16* slots, uint64_t nslots) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nheads) return;
+    const uint32_t r = heads[j], full = pbytes >> 3, rem = pbytes & 7;
+    unsigned long long w[2] = {0, 0};
+    for (uint32_t i = 0; i < full; i++) w[i] = image[(uint64_t)i * n + r];
+    if (rem) w[full] = image[(uint64_t)full * n + r] & (~0ull << (8 * (8 - rem)));
+    uint64_t s = slot_of(hash3(w[0], w[1], 0ull), nslots);
+    for (;;) {
+        if (atomicCAS(&slots[s].row1, 0u, r + 1u) == 0u) { slots[s].k0 = w[0]; slots[s].k1 = (uint32_t)(w[1] >> 32); return; }
+        if (++s == nslots) s = 0;
+    }
+}
+__global__ void __launch_bounds__(256) join_probe16_kernel(KeyDesc kd, uint64_t np, const Slot16* __restrict__ slots, uint64_t nslots,
+                                                           uint32_t* lo, uint32_t* cnt, uint32_t* not_one) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long w0, w1, w2;
+        pack3(kd, i, w0, w1, w2);
+        uint64_t s = slot_of(hash3(w0, w1, 0ull), nslots);
+        uint32_t l = 0, c = 0;
+        for (;;) {
+            const uint4 sl = __ldg(reinterpret_cast<const uint4*>(&slots[s]));
+            if (sl.w == 0u) break;
+            if (sl.x == (uint32_t)w0 && sl.y == (uint32_t)(w0 >> 32) && sl.z == (uint32_t)(w1 >> 32)) { l = sl.w - 1u; c = 1u; break; }
             if (++s == nslots) s = 0;
         }
         lo[i] = l; cnt[i] = c;
@@ -206,7 +263,16 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
                                                                         ht.slots->as<uint32_t>(), ht.nslots - 1);
         CPB_CUDA(cudaGetLastError());
     }
-    if (ht.pbytes <= 24 && (ht.nslots + ht.nheads + 1) * 4 > 200 * 1024) {  // too large for smem, key fits a sector
+    const bool too_large_for_smem = (ht.nslots + ht.nheads + 1) * 4 > 200 * 1024;
+    if (ht.pbytes <= 12 && ht.nheads == n && too_large_for_smem) {  // unique short keys: 16-byte slots
+        ht.nslots16 = ht.nheads * 2 + 16;
+        ht.slots16 = dev_alloc(c, ht.nslots16 * sizeof(Slot16));
+        CPB_CUDA(cudaMemsetAsync(ht.slots16->p, 0, ht.nslots16 * sizeof(Slot16), c->stream));
+        KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8) + ht.nslots16 * 16);
+        hash16_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
+                                                                          ht.slots16->as<Slot16>(), ht.nslots16);
+        CPB_CUDA(cudaGetLastError());
+    } else if (ht.pbytes <= 24 && too_large_for_smem) {  // key fits a sector
         ht.nslots32 = ht.nheads + ht.nheads / 2 + 16;
         ht.slots32 = dev_alloc(c, ht.nslots32 * sizeof(Slot32));
         CPB_CUDA(cudaMemsetAsync(ht.slots32->p, 0, ht.nslots32 * sizeof(Slot32), c->stream));
@@ -259,13 +325,18 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
         std::vector<uint32_t> widths(ix.key_width.begin(), ix.key_width.begin() + nk);
         uint32_t pwords = 0;
         Buf pimg;
-        if (!ht.slots32) pimg = pack_with_widths(c, probe, pidx, widths, &pwords);
+        if (!ht.slots32 && !ht.slots16) pimg = pack_with_widths(c, probe, pidx, widths, &pwords);
         else pwords = (ht.pbytes + 7) / 8;
         // algorithmic bytes: probe keys once + build table once
         uint64_t algo = np * ((uint64_t)pwords * 8 + 8) + ht.nslots * 4 + ht.nheads * ((uint64_t)ht.pbytes + 4);
         size_t smem = (ht.nslots + ht.nheads + 1) * 4;
         KernelTimer kt(c, "join_probe", algo);
-        if (ht.slots32) {
+        if (ht.slots16) {
+            KeyDesc kd{};
+            describe_keys(c, probe, pidx, widths, kd);
+            uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
+            join_probe16_kernel<<<grid, 256, 0, c->stream>>>(kd, np, ht.slots16->as<Slot16>(), ht.nslots16, lo->as<uint32_t>(), cnt->as<uint32_t>(), not_one);
+        } else if (ht.slots32) {
             KeyDesc kd{};
             describe_keys(c, probe, pidx, widths, kd);
             uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);

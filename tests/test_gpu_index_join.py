@@ -339,3 +339,31 @@ def test_join_row_slot_path_and_fallbacks(shape):
     exact = _kv_csv(["pid", "k2"], [[str(j), str(rng.randrange(nidx))] for j in range(nprobe)])
     te, _ = cp.Take(cp.FromBytes(exact))._table()
     assert_table_equals_oracle(te.join(uidx, "k2"), orc.reader_rows(exact).join(orc.reader_rows(udata).unique_index_on("k"), "k2"))
+
+
+@pytest.mark.parametrize("shape", ["nonunique_slot32", "wide_key_generic"])
+def test_join_large_index_other_probe_tables(shape):
+    """large indices that cannot use the 16-byte unique-key slots: non-unique keys (32-byte slots with run lengths)
+    and key prefixes wider than 24 bytes (slot -> heads -> image probe in global memory)"""
+    import csvplus_b200 as cp
+    ctx = gpu_ctx()
+    ncust = 120_000
+    cust = ctx.gen_csv("customers", (0, ncust), n_cust=ncust, permute=True)
+    orders = ctx.gen_csv("orders", (0, 200_000), n_cust=ncust, n_prod=100)
+    tc, _ = cp.parse_csv(ctx, cust, spec=[("id", -1), ("name", -1), ("surname", -1)])
+    to, _ = cp.parse_csv(ctx, orders, spec=[("cust_id", -1), ("prod_id", -1), ("qty", -1), ("ts", -1)])
+    oc = orc.reader_rows(cust.to_host(), select=["id", "name", "surname"])
+    oo = orc.reader_rows(orders.to_host(), select=["cust_id", "prod_id", "qty", "ts"])
+    if shape == "nonunique_slot32":
+        idx = to.index_on("cust_id")
+        j = tc.join(idx, "id")
+        oj = oc.join(oo.index_on("cust_id"), "id")
+        assert len(oj) > 150_000
+    else:
+        idx = to.index_on("ts", "cust_id", "prod_id")
+        probe, _ = cp.parse_csv(ctx, orders, spec=[("ts", -1), ("cust_id", -1), ("prod_id", -1), ("order_id", -1)])
+        j = probe.join(idx, "ts", "cust_id", "prod_id")
+        op = orc.reader_rows(orders.to_host(), select=["ts", "cust_id", "prod_id", "order_id"])
+        oj = op.join(oo.index_on("ts", "cust_id", "prod_id"), "ts", "cust_id", "prod_id")
+        assert len(oj) >= 200_000
+    assert_table_equals_oracle(j, oj)
