@@ -35,21 +35,28 @@ const char* kind_text(int k) {
     }
 }
 
-template <int KMAX, bool EXACT>
-void launch_scan(Ctx* c, const ParseParams& P, uint64_t algo_bytes) {
+template <int KMAX, bool EXACT, bool HP>
+void launch_scan_hp(Ctx* c, const ParseParams& P, uint64_t algo_bytes) {
     static bool configured = false;
     const size_t smem = sizeof(ParseSmem);
     if (!configured) {
-        CPB_CUDA(cudaFuncSetAttribute(csv_scan_kernel<KMAX, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CPB_CUDA(cudaFuncSetAttribute(csv_scan_kernel<KMAX, EXACT, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int occ = 0;
-    CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, csv_scan_kernel<KMAX, EXACT>, THREADS, smem));
+    CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, csv_scan_kernel<KMAX, EXACT, HP>, THREADS, smem));
     if (occ < 1) occ = 1;
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count * occ, P.ntiles);
     KernelTimer kt(c, "csv_scan", algo_bytes);
-    csv_scan_kernel<KMAX, EXACT><<<grid, THREADS, smem, c->stream>>>(P);
+    csv_scan_kernel<KMAX, EXACT, HP><<<grid, THREADS, smem, c->stream>>>(P);
     CPB_CUDA(cudaGetLastError());
+}
+
+// unfiltered parses run kernels compiled without any Like-comparison code
+template <int KMAX, bool EXACT>
+void launch_scan(Ctx* c, const ParseParams& P, uint64_t algo_bytes) {
+    if (EXACT && P.pred.nops == 0) launch_scan_hp<KMAX, EXACT, false>(c, P, algo_bytes);
+    else launch_scan_hp<KMAX, EXACT, true>(c, P, algo_bytes);
 }
 
 }  // namespace

@@ -224,7 +224,7 @@ __global__ void g_rec_count(ParseParams P, GenOpts o, const unsigned long long* 
     Rec<MAXSEL> r;
     r.err = s.err; r.nf = s.nfields; r.present = sink.present; r.eq = sink.eq; r.slow = true; r.err_slot = 0;
     for (int k = 0; k < MAXSEL; k++) r.f[k] = (k < P.nsel && ((sink.present >> k) & 1)) ? sink.ulen[k] : 0;
-    finish_record<MAXSEL, false>(P, r);
+    finish_record<MAXSEL, false, true>(P, r);
     bool ok = r.err == K_OK && eval_pred(P.pred, r.eq);
     if (r.err != K_OK) atomicMin(&P.result->err_key, (unsigned long long)((i << 16) | ((uint32_t)r.err << 8) | (uint32_t)r.err_slot));
     flag[i] = ok ? 1u : 0u;

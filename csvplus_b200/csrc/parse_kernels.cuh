@@ -21,8 +21,17 @@
 
 // A/B switches measured on B200 (tools/time_parse.py, 20 M rows): drawing the next tile's ticket early lengthens the
 // look-back distance (656 vs 720 GB/s); word-wise staging copies lose to the byte loop on short fields (510 vs 528 GB/s).
+// Also measured and rejected (40 M rows; filter / orders / all-columns GB/s, baseline 738 / 555 / 371):
+//   * one stage for all columns, owners copy their rows, direct offset stores (2 barriers per tile instead of 4 per
+//     column): 691 / 583 / 377 -- the barriers are not the cost, the byte loop is;
+//   * folding the parity verification and the any-slow vote into the block scan's barrier: 548 / 420 / 292.
 #ifndef CPB_EARLY_TICKET
 #define CPB_LATE_TICKET 1
+#endif
+#ifdef CPB_RT_KLOOP
+#define CPB_KLOOP_PRAGMA _Pragma("unroll 1")
+#else
+#define CPB_KLOOP_PRAGMA _Pragma("unroll")
 #endif
 
 namespace cpb {
@@ -283,7 +292,8 @@ __device__ __forceinline__ int next_set(const uint32_t* bm, int from, int lim) {
         m = bm[wi];
     }
 }
-__device__ __forceinline__ int count_bits(const uint32_t* bm, int a, int b) {  // bits set in [a,b)
+// (out of line: only tiles that contain quotes call it, and it would be inlined once per cached line)
+static __device__ __noinline__ int count_bits(const uint32_t* bm, int a, int b) {  // bits set in [a,b)
     if (a >= b) return 0;
     int wa = a >> 5, wb = b >> 5;
     uint32_t ma = 0xffffffffu << (a & 31);
@@ -376,7 +386,9 @@ struct Rec {
 };
 
 // record-level checks in the reference's order: parse error (already set) > field count > missing column
-template <int KMAX, bool EXACT>
+// HP ("has predicate") = false compiles every Like comparison out: the kernels of unfiltered parses carry no
+// literal-compare code between their hot loops (the kernel is instruction-fetch sensitive).
+template <int KMAX, bool EXACT, bool HP>
 __device__ __forceinline__ void finish_record(const ParseParams& P, Rec<KMAX>& r) {
     if (r.err != K_OK) return;
     if (P.expect_fields > 0 && r.nf != P.expect_fields) { r.err = K_FIELDS; return; }
@@ -384,7 +396,7 @@ __device__ __forceinline__ void finish_record(const ParseParams& P, Rec<KMAX>& r
     uint32_t missing = want & ~r.present;
     if (missing) {
         if (P.pad_missing) {  // padded "" values still take part in Like comparisons against empty literals
-            uint32_t m = missing;
+            uint32_t m = HP ? missing : 0u;
             while (m) {
                 int k = __ffs(m) - 1; m &= m - 1;
                 uint32_t tm = P.slot_terms[k];
@@ -404,7 +416,7 @@ __device__ __forceinline__ void run_slow(const ParseParams& P, const ByteSrc& sr
 }
 
 // Line `i` of the window through the flat structural index.  Returns false when it is not a record.
-template <int KMAX, bool EXACT>
+template <int KMAX, bool EXACT, bool HP>
 __device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem& sm, const ByteSrc& src, const uint8_t* lits,
                                           bool lits_in_smem, uint64_t tile_base, int i, int nterm, int rel_n, int64_t rel_ds, bool tile_has_q,
                                           Rec<KMAX>& r) {
@@ -437,7 +449,7 @@ __device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem&
                     const uint32_t len = (uint32_t)(fe - fb);
                     r.f[k] = (uint32_t)fb | (len << 16);
                     r.present |= 1u << k;
-                    uint32_t tm = P.slot_terms[k];
+                    uint32_t tm = HP ? P.slot_terms[k] : 0u;
                     while (tm) {
                         int t = __ffs(tm) - 1; tm &= tm - 1;
                         if (len == P.pred.term_len[t]) {
@@ -450,12 +462,12 @@ __device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem&
             }
         }
     }
-    finish_record<KMAX, EXACT>(P, r);
+    finish_record<KMAX, EXACT, HP>(P, r);
     return true;
 }
 
 // Dense-tile fallback: the record starting at window offset ws, always through the sequential machine.
-template <int KMAX, bool EXACT>
+template <int KMAX, bool EXACT, bool HP>
 __device__ __forceinline__ bool generic_record(const ParseParams& P, const ParseSmem& sm, const ByteSrc& src, uint64_t tile_base,
                                                int ws, int rel_n, Rec<KMAX>& r) {
     // empty line: "\n", "\r\n", or a lone "\r" right before EOF
@@ -464,7 +476,7 @@ __device__ __forceinline__ bool generic_record(const ParseParams& P, const Parse
     if (c0 == '\r' && (sm.data[PRE + ws + 1] == '\n' || ws + 1 >= rel_n)) return false;
     r.present = 0; r.eq = 0; r.err = K_OK; r.err_slot = 0;
     run_slow<KMAX, EXACT>(P, src, tile_base + ws, r);
-    finish_record<KMAX, EXACT>(P, r);
+    finish_record<KMAX, EXACT, HP>(P, r);
     return true;
 }
 
@@ -627,7 +639,7 @@ __device__ __forceinline__ void lookback_totals_w0(const unsigned long long* wor
     if (lane < NP) sm.tile_prefix[lane] = excl;
 }
 
-template <int KMAX, bool EXACT>
+template <int KMAX, bool EXACT, bool HP>
 __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ParseSmem& sm = *reinterpret_cast<ParseSmem*>(smem_raw);
@@ -847,7 +859,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
             bool survived = false;
             if (r.err != K_OK) {
                 if (my_err == 0xffffffffu) { my_err = (nrec << 16) | ((uint32_t)r.err << 8) | (uint32_t)r.err_slot; err_rows_local = nrow; }
-            } else if (eval_pred(P.pred, r.eq)) {
+            } else if (!HP || eval_pred(P.pred, r.eq)) {
                 if (nrow == 0) first_surv_rec = nrec;
                 nrow++;
                 survived = true;
@@ -870,7 +882,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 const int i = i0 + tid * L + q;
                 if (q < L && i <= m_last) {
                     Rec<KMAX> r;
-                    if (flat_line<KMAX, EXACT>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
+                    if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
                         const bool surv = account(r);
                         if (r.slow) any_slow = true;
                         else if (surv) {
@@ -885,7 +897,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 const int i = i0 + tid * L + q;
                 if (i > m_last) break;
                 Rec<KMAX> r;
-                if (flat_line<KMAX, EXACT>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
+                if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
             }
         } else {
 #pragma unroll 1
@@ -894,7 +906,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 while (m) {
                     int b = __ffs(m) - 1; m &= m - 1;
                     Rec<KMAX> r;
-                    if (generic_record<KMAX, EXACT>(P, sm, src, tile_base, (tid * WPT + j) * 32 + b, rel_n, r)) account(r);
+                    if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, (tid * WPT + j) * 32 + b, rel_n, r)) account(r);
                 }
             }
         }
@@ -992,15 +1004,26 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 const uint64_t row_base = sm.tile_prefix[1];
                 const uint32_t osh = (uint32_t)(row_base & 3);
                 if (nrow != 0 && row == 0) P.result->first_row_ordinal = rec0 + first_surv_rec;
-#pragma unroll
+                // (CPB_RT_KLOOP runs the column loop at run time -- one copy of the staging code instead of KMAX, the
+                // register-resident per-column values picked by select chains; measured slower: 679 vs 736 GB/s)
+                CPB_KLOOP_PRAGMA
                 for (int k = 0; k < KMAX; k++) {
                     if (k < (EXACT ? KMAX : P.nsel)) {
                         const uint64_t dbase = sm.tile_prefix[2 + k];
+                        uint32_t myf[RC], exk_k = 0, totk_k = 0;
+#pragma unroll
+                        for (int kk = 0; kk < KMAX; kk++) if (kk == k) { exk_k = exk[kk]; totk_k = totk[kk]; }
+#pragma unroll
+                        for (int q = 0; q < RC; q++) {
+                            myf[q] = 0;
+#pragma unroll
+                            for (int kk = 0; kk < KMAX; kk++) if (kk == k) myf[q] = cf[q][kk];
+                        }
                         {
-                            uint32_t j = ex0 >> 16, run = exk[k];
+                            uint32_t j = ex0 >> 16, run = exk_k;
 #pragma unroll
                             for (int q = 0; q < RC; q++)
-                                if ((cmask >> q) & 1) { ost[osh + j] = (uint32_t)(dbase + run); wl[j] = cf[q][k]; j++; run += cf[q][k] >> 16; }
+                                if ((cmask >> q) & 1) { ost[osh + j] = (uint32_t)(dbase + run); wl[j] = myf[q]; j++; run += myf[q] >> 16; }
                         }
                         __syncthreads();
                         // ---- offsets of this tile's rows
@@ -1019,7 +1042,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                             }
                         }
                         // ---- field bytes
-                        const uint32_t B = totk[k];
+                        const uint32_t B = totk_k;
                         const uint32_t r16 = (uint32_t)(dbase & 15);
                         const uint64_t room = P.data_cap[k] > dbase ? P.data_cap[k] - dbase : 0;
                         const uint32_t hi_ok = r16 + (uint32_t)(B < room ? B : room);  // shifted local end of writable bytes
@@ -1063,7 +1086,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 for (int k = 0; k < KMAX; k++) off[k] = k < (EXACT ? KMAX : P.nsel) ? sm.tile_prefix[2 + k] + exk[k] : 0;
                 uint32_t rec_local = 0;
                 auto emit = [&](const Rec<KMAX>& r, uint64_t start_abs) {
-                    if (r.err != K_OK || !eval_pred(P.pred, r.eq)) { rec_local++; return; }
+                    if (r.err != K_OK || (HP && !eval_pred(P.pred, r.eq))) { rec_local++; return; }
                     if (row == 0) P.result->first_row_ordinal = rec0 + rec_local;
                     const bool row_ok = row < P.row_cap;
                     if (r.slow) {
@@ -1094,7 +1117,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                         const int i = i0 + tid * L + q;
                         if (i > m_last) break;
                         Rec<KMAX> r;
-                        if (flat_line<KMAX, EXACT>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
+                        if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
                             emit(r, tile_base + (i == 0 ? 0 : (uint64_t)sm.sidx[sm.ord[i - 1]] + 1));
                     }
                 } else {
@@ -1105,7 +1128,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                             int b = __ffs(m) - 1; m &= m - 1;
                             const int ws = (tid * WPT + j) * 32 + b;
                             Rec<KMAX> r;
-                            if (generic_record<KMAX, EXACT>(P, sm, src, tile_base, ws, rel_n, r)) emit(r, tile_base + ws);
+                            if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, ws, rel_n, r)) emit(r, tile_base + ws);
                         }
                     }
                 }
