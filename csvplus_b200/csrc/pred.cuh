@@ -23,9 +23,8 @@ struct PredProg {
     int32_t term_col[MAXTERMS];   // column (table filter) or extracted slot (fused parse)
 };
 
-__device__ __forceinline__ bool eval_pred(const PredProg& pr, uint32_t eq) {
-    if (pr.nops == 0) return true;
-    if (pr.nops == 1 && pr.op[0] == OP_TERM) return (eq >> pr.arg[0]) & 1;
+// general case out of line (the parse kernel would inline the interpreter once per cached line)
+static __device__ __noinline__ bool eval_pred_general(const PredProg& pr, uint32_t eq) {
     uint64_t st = 0;  // bit stack
     for (int i = 0; i < pr.nops; i++) {
         switch (pr.op[i]) {
@@ -38,6 +37,11 @@ __device__ __forceinline__ bool eval_pred(const PredProg& pr, uint32_t eq) {
         }
     }
     return st & 1;
+}
+__device__ __forceinline__ bool eval_pred(const PredProg& pr, uint32_t eq) {
+    if (pr.nops == 0) return true;
+    if (pr.nops == 1 && pr.op[0] == OP_TERM) return (eq >> pr.arg[0]) & 1;
+    return eval_pred_general(pr, eq);
 }
 
 struct Compiled {
