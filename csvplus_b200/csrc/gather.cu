@@ -138,6 +138,17 @@ __device__ __forceinline__ void copy_unaligned(uint8_t* q, const uint8_t* sp, ui
         for (uint32_t b = 0; b < 8; b++) if (b < rem) q[k + b] = (uint8_t)(v >> (8 * b));
     }
 }
+// Writes stage bytes [sh, end) to gb (16-byte aligned, laid out like the stage): whole vectors with 16-byte
+// stores, the partial first / last vector one byte per lane (lanes 0-15 / 16-31) -- no lane loops over bytes.
+__device__ __forceinline__ void warp_store_stage(uint8_t* gb, const uint8_t* stage, uint32_t sh, uint32_t end, int lane) {
+    for (uint32_t x = lane * 16; x + 16 <= end; x += 32 * 16)
+        if (x >= sh) *reinterpret_cast<uint4*>(gb + x) = *reinterpret_cast<const uint4*>(stage + x);
+    const uint32_t t0 = end & ~15u;
+    const bool head = lane < 16;
+    const uint32_t y = head ? (uint32_t)lane : t0 + (uint32_t)(lane - 16);
+    const bool on = head ? sh != 0 : ((end & 15u) != 0 && (t0 != 0 || sh == 0));
+    if (on && y >= sh && y < end) gb[y] = stage[y];
+}
 constexpr int GW_WARPS = 8;
 constexpr int GW_STAGE = 2048;  // bytes staged per warp; longer groups take the direct path
 __global__ void __launch_bounds__(GW_WARPS * 32) gather_copy_kernel(const uint32_t* __restrict__ src_off, const uint8_t* __restrict__ src,
@@ -162,11 +173,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32) gather_copy_kernel(const uint32
         if (sh + total <= GW_STAGE) {
             copy_unaligned(stage + sh + (d - d0), sp, len);
             __syncwarp();
-            uint8_t* gb = dst + (d0 - sh);
-            for (uint32_t x = lane * 16; x < sh + total; x += 32 * 16) {
-                if (x >= sh && x + 16 <= sh + total) *reinterpret_cast<uint4*>(gb + x) = *reinterpret_cast<const uint4*>(stage + x);
-                else for (uint32_t y = x; y < x + 16; y++) if (y >= sh && y < sh + total) gb[y] = stage[y];
-            }
+            warp_store_stage(dst + (d0 - sh), stage, sh, sh + total, lane);
             __syncwarp();
         } else {
             copy_unaligned(dst + d, sp, len);
@@ -407,7 +414,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32) slot_copy_kernel(const uint8_t*
                 uint8_t* q = stage + sh + (d - d0);
                 for (uint32_t k = 0; k < len; k++) q[k] = sp[k];
                 __syncwarp();
-                uint8_t* gb = dst + (d0 - sh);
+                uint8_t* gb = dst + (d0 - sh);  // (warp_store_stage measured slower here: 4.25 vs 3.94 ms per 100 M rows)
                 for (uint32_t x = lane * 16; x < sh + total; x += 32 * 16) {
                     if (x >= sh && x + 16 <= sh + total) *reinterpret_cast<uint4*>(gb + x) = *reinterpret_cast<const uint4*>(stage + x);
                     else for (uint32_t y = x; y < x + 16; y++) if (y >= sh && y < sh + total) gb[y] = stage[y];
