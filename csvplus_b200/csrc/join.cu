@@ -65,6 +65,12 @@ __global__ void hash_insert_kernel(const uint64_t* __restrict__ image, uint64_t 
     }
 }
 
+// total number of matches (= join result rows), one atomic per warp: flags layout [0..1] scan total, [2] not_one,
+// [4..5] matches.  With it a join whose probe rows all match exactly once needs no scan of the counts at all.
+__device__ __forceinline__ void add_matches(uint32_t* not_one, unsigned long long matches) {
+    matches = warp_sum_u64(matches);
+    if ((threadIdx.x & 31) == 0 && matches) atomicAdd(reinterpret_cast<unsigned long long*>(not_one + 2), matches);
+}
 // probe: per probe row the matching run of sorted index rows: lo[i], cnt[i] (cnt 0 = no match)
 template <bool SMEM>
 __global__ void __launch_bounds__(256) join_probe_kernel(const uint64_t* __restrict__ pimg, uint64_t np, const uint64_t* __restrict__ iimg,
@@ -81,6 +87,7 @@ __global__ void __launch_bounds__(256) join_probe_kernel(const uint64_t* __restr
         slots = sh; heads = sh + nslots;
     }
     const uint64_t mask = nslots - 1;
+    unsigned long long matches = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t s = hash_prefix(pimg, np, i, pbytes) & mask;
         uint32_t l = 0, c = 0;
@@ -91,9 +98,10 @@ __global__ void __launch_bounds__(256) join_probe_kernel(const uint64_t* __restr
             if (prefix_equal2(pimg, np, i, iimg, ni, r, pbytes)) { l = r; c = heads[j + 1] - r; break; }
             s = (s + 1) & mask;
         }
-        lo[i] = l; cnt[i] = c;
+        lo[i] = l; cnt[i] = c; matches += c;
         if (__any_sync(__activemask(), c != 1) && c != 1) *not_one = 1u;  // benign race: every writer stores 1
     }
+    add_matches(not_one, matches);
 }
 
 // ------------------------------------------------------------------ embedded-key table (key prefixes <= 24 bytes)
@@ -162,6 +170,7 @@ __device__ __forceinline__ void pack3(const KeyDesc& kd, uint64_t r, unsigned lo
 }
 __global__ void __launch_bounds__(256) join_probe32_kernel(KeyDesc kd, uint64_t np, const Slot32* __restrict__ slots, uint64_t nslots,
                                                            uint32_t* lo, uint32_t* cnt, uint32_t* not_one) {
+    unsigned long long matches = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
         unsigned long long w0, w1, w2;
         pack3(kd, i, w0, w1, w2);
@@ -173,9 +182,10 @@ __global__ void __launch_bounds__(256) join_probe32_kernel(KeyDesc kd, uint64_t 
             if (sl.x == w0 && sl.y == w1 && sl.z == w2) { l = (uint32_t)sl.w; c = (uint32_t)(sl.w >> 32); break; }
             if (++s == nslots) s = 0;
         }
-        lo[i] = l; cnt[i] = c;
+        lo[i] = l; cnt[i] = c; matches += c;
         if (c != 1) *not_one = 1u;  // benign race: every writer stores 1
     }
+    add_matches(not_one, matches);
 }
 
 // 16-byte slots for key prefixes <= 12 bytes whose runs all have length 1 (unique keys): four slots per 64-byte
@@ -197,6 +207,7 @@ __global__ void hash16_insert_kernel(const uint64_t* __restrict__ image, uint64_
 }
 __global__ void __launch_bounds__(256) join_probe16_kernel(KeyDesc kd, uint64_t np, const Slot16* __restrict__ slots, uint64_t nslots,
                                                            uint32_t* lo, uint32_t* cnt, uint32_t* not_one) {
+    unsigned long long matches = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (uint64_t)gridDim.x * blockDim.x) {
         unsigned long long w0, w1, w2;
         pack3(kd, i, w0, w1, w2);
@@ -208,9 +219,10 @@ __global__ void __launch_bounds__(256) join_probe16_kernel(KeyDesc kd, uint64_t 
             if (sl.x == (uint32_t)w0 && sl.y == (uint32_t)(w0 >> 32) && sl.z == (uint32_t)(w1 >> 32)) { l = sl.w - 1u; c = 1u; break; }
             if (++s == nslots) s = 0;
         }
-        lo[i] = l; cnt[i] = c;
+        lo[i] = l; cnt[i] = c; matches += c;
         if (c != 1) *not_one = 1u;  // benign race: every writer stores 1
     }
+    add_matches(not_one, matches);
 }
 
 __global__ void expand_pairs_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ pos,
@@ -255,9 +267,12 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
     compact_heads_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(head->as<uint32_t>(), pos->as<uint32_t>(), ht.heads->as<uint32_t>(), n);
     uint64_t want = std::max<uint64_t>(16, ht.nheads * 2);
     ht.nslots = 1; while (ht.nslots < want) ht.nslots <<= 1;
-    ht.slots = dev_alloc(c, ht.nslots * 4);
-    CPB_CUDA(cudaMemsetAsync(ht.slots->p, 0xff, ht.nslots * 4, c->stream));
-    {
+    // one of three probe tables: ordinal slots (+ heads + key image; shared-memory sized or wide keys), or the
+    // embedded-key 16 / 32 byte slots
+    const bool large = (ht.nslots + ht.nheads + 1) * 4 > 200 * 1024;
+    if (!(large && ht.pbytes <= 24)) {
+        ht.slots = dev_alloc(c, ht.nslots * 4);
+        CPB_CUDA(cudaMemsetAsync(ht.slots->p, 0xff, ht.nslots * 4, c->stream));
         KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8));
         hash_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
                                                                         ht.slots->as<uint32_t>(), ht.nslots - 1);
@@ -315,8 +330,8 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
         return gather_rows(c, e, nullptr, 0);
     };
     if (np == 0) return empty_result();
-    Buf lo = dev_alloc(c, np * 4), cnt = dev_alloc(c, (np + 1) * 4), flags = dev_alloc(c, 16);
-    CPB_CUDA(cudaMemsetAsync(flags->p, 0, 16, c->stream));
+    Buf lo = dev_alloc(c, np * 4), cnt = dev_alloc(c, (np + 1) * 4), flags = dev_alloc(c, 32);
+    CPB_CUDA(cudaMemsetAsync(flags->p, 0, 32, c->stream));
     uint32_t* not_one = flags->as<uint32_t>() + 2;  // [0..1] = scan total
     if (ni == 0) {
         CPB_CUDA(cudaMemsetAsync(cnt->p, 0, (np + 1) * 4, c->stream));
@@ -369,14 +384,12 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
         r->first_line = probe.first_line;
         return r;
     }
-    Buf pos = dev_alloc(c, (np + 1) * 4);
-    exclusive_scan_u32(c, cnt->as<uint32_t>(), pos->as<uint32_t>(), np, tot->as<uint64_t>());
-    uint32_t* hf = (uint32_t*)c->pinned_scratch(16);
-    CPB_CUDA(cudaMemcpyAsync(hf, flags->p, 16, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t* hf = (uint32_t*)c->pinned_scratch(32);
+    CPB_CUDA(cudaMemcpyAsync(hf, flags->p, 32, cudaMemcpyDeviceToHost, c->stream));
     CPB_CUDA(cudaStreamSynchronize(c->stream));
-    const uint64_t m = (uint64_t)hf[0] | ((uint64_t)hf[1] << 32);
+    const uint64_t m = (uint64_t)hf[4] | ((uint64_t)hf[5] << 32);  // counted by the probe kernel (0 when ni == 0)
     // every probe row matched exactly one index row (the usual foreign-key join): the probe-side columns of the
-    // result ARE the probe columns, in order — share their buffers instead of copying them
+    // result ARE the probe columns, in order — share their buffers instead of copying them; no scan of the counts
     const bool probe_identity = ni != 0 && hf[2] == 0 && m == np;
     if (m > 0xfffffffeull) throw DataError{CPB_E_TOO_LARGE, -1, 0, false, "join result exceeds 2^32-2 rows; probe in smaller batches"};
     if (m == 0) return empty_result();
@@ -387,6 +400,8 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
         for (auto* p : pcols) out->cols.push_back(*p);
         return out;
     }
+    Buf pos = dev_alloc(c, (np + 1) * 4);
+    exclusive_scan_u32(c, cnt->as<uint32_t>(), pos->as<uint32_t>(), np, tot->as<uint64_t>());
     Buf pid = dev_alloc(c, m * 4), iid = dev_alloc(c, m * 4);
     {
         KernelTimer kt(c, "join_pairs", np * 12 + m * 8);
