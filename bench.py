@@ -152,6 +152,25 @@ CUST_ROWS = 10_000_000
 PEOPLE_ROWS = 100_000_000
 
 
+def ncu_traffic(path: str):
+    """mean dram__bytes_read.sum + dram__bytes_write.sum per csv_scan launch from the committed ncu metrics pass of this
+    bench command's join step (profiles/r1_traffic_csv_scan.csv: the customers and the orders parse); None if absent"""
+    import csv
+    try:
+        per_id = {}
+        with open(path) as f:
+            rows = [r for r in csv.reader(f) if len(r) > 14]
+        hdr = rows[0]
+        ki, mi, ui, vi, ii = (hdr.index(x) for x in ("Kernel Name", "Metric Name", "Metric Unit", "Metric Value", "ID"))
+        for r in rows[1:]:
+            if "csv_scan" in r[ki] and r[mi] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r[ui]]
+                per_id[r[ii]] = per_id.get(r[ii], 0.0) + float(r[vi].replace(",", "")) * scale
+        return sum(per_id.values()) / len(per_id) if per_id else None
+    except Exception:
+        return None
+
+
 def bind_to_gpu_numa_node(local: int):
     """Pin this process (and the pinned host buffers it allocates afterwards) to the NUMA node the GPU hangs off,
     so that H2D copies do not cross the socket interconnect.  Best effort: silently skipped where /sys is not
@@ -297,7 +316,7 @@ def main():
         per_launch_ms = s["ms"] / s["launches"]
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": "csv_scan", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_kind": f"of {peak_kind}", "launches": s["launches"], "ms_per_launch": per_launch_ms,
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r1_traffic_csv_scan.csv)", "peak_kind": f"of {peak_kind}", "launches": s["launches"], "ms_per_launch": per_launch_ms,
                 "algo_bytes_per_launch": per_launch_bytes}
 
     # ---------------- end-to-end timing from pinned host buffers
@@ -428,7 +447,7 @@ def main():
             "config": workload_config(world),
             "clocks": clocks, "gpu_launches": launches, "out_rows_per_gpu": out_rows,
             "e2e": e2e,
-            "roofline": roof(st_join),
+            "roofline": roof(st_join, ncu_traffic(os.path.join(ROOT, "profiles", "r1_traffic_csv_scan.csv")) if world == 1 else None),
             "csv_parse": {"metric": "CSV parse GB/s (configs[1]: parse+SelectColumns(name,surname,id)+Filter(Like name=Amelia))",
                           "value": world * d_people.nbytes / (ms_parse * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_parse,
                           "rows_per_s": world * PEOPLE_ROWS / (ms_parse * 1e-3), "rows_out_per_gpu": parse_rows,
