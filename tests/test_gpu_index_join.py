@@ -367,3 +367,39 @@ def test_join_large_index_other_probe_tables(shape):
         oj = op.join(oo.index_on("ts", "cust_id", "prod_id"), "ts", "cust_id", "prod_id")
         assert len(oj) >= 200_000
     assert_table_equals_oracle(j, oj)
+
+
+def test_join_scale_property_id_equals_cust_id():
+    """BASELINE-size shape at 20 M x 2 M rows (too large for the oracle): size-independent properties of a
+    foreign-key join — every probe row survives in order (the probe columns are shared, not copied), and the
+    index-side key column gathered through the row slots is byte-identical to the probe key column"""
+    import torch
+    import csvplus_b200 as cp
+    from csvplus_b200.dist import _as_tensor
+    ctx = gpu_ctx()
+    ncust, nord = 2_000_000, 20_000_000
+    cust = ctx.gen_csv("customers", (0, ncust), n_cust=ncust, permute=True)
+    orders = ctx.gen_csv("orders", (0, nord), n_cust=ncust, n_prod=1000)
+    tc, _ = cp.parse_csv(ctx, cust, spec=[("id", -1), ("name", -1), ("surname", -1)])
+    to, _ = cp.parse_csv(ctx, orders, spec=[("cust_id", -1), ("prod_id", -1), ("qty", -1), ("ts", -1)])
+    assert len(tc) == ncust and len(to) == nord
+    idx = tc.index_on("id", unique=True)
+    j = to.join(idx, "cust_id")
+    assert len(j) == nord
+    ctx.sync()
+
+    def col(t, name):
+        po, pd = t.device_column(name)
+        off = _as_tensor(po, 4 * (len(t) + 1)).view(torch.int32)
+        return off, _as_tensor(pd, int(off[-1].item()))
+    oi, di = col(j, "id")
+    oc, dc = col(j, "cust_id")
+    assert torch.equal(oi, oc) and torch.equal(di, dc)
+    # the probe columns of an exact-once join are the probe table's own buffers
+    assert j.device_column("ts") == to.device_column("ts")
+    # sorted index: ids ascending bytewise (sortedness) and a permutation of the input (same multiset of lengths)
+    st = idx.table()
+    so, sd = col(st, "id")
+    uo, ud = col(tc, "id")
+    assert torch.equal(torch.sort(so[1:] - so[:-1]).values, torch.sort(uo[1:] - uo[:-1]).values)
+    assert int(sd.sum(dtype=torch.int64).item()) == int(ud.sum(dtype=torch.int64).item())
