@@ -77,12 +77,38 @@ def _as_tensor(ptr: int, nbytes: int):
     return torch.as_tensor(_DevArr(ptr, nbytes), device="cuda")[:nbytes]
 
 
-def allgather_table(ctx, table, dist, group=None):
-    """every rank contributes its rows; returns the concatenation of all ranks' rows (rank order) on every rank"""
-    import torch
+class _PendingGather:
+    """an all-gather of a table in flight (allgather_table_async): the collective is enqueued on torch's current
+    stream; wait() blocks until it is done and assembles the concatenated table"""
 
-    from . import _abi
-    from .api import Table, _raise, _strs
+    def __init__(self, ctx, cols, parts, event, world, keep):
+        self.ctx, self.cols, self.parts, self.event, self.world, self.keep = ctx, cols, parts, event, world, keep
+
+    def wait(self):
+        from .api import Table, _raise, _strs
+        ctx, cols, parts = self.ctx, self.cols, self.parts
+        self.event.synchronize()
+        names, keep = _strs(cols)
+        tabs = []
+        for r in range(self.world):
+            rows = parts[r][0].numel() // 4 - 1
+            oa = (C.c_void_p * len(cols))(*[parts[r][2 * k].data_ptr() for k in range(len(cols))])
+            da = (C.c_void_p * len(cols))(*[parts[r][2 * k + 1].data_ptr() if parts[r][2 * k + 1].numel() else 0
+                                            for k in range(len(cols))])
+            h = C.c_void_p()
+            st = ctx.lib.cpb_table_from_device(ctx.h, len(cols), names, oa, da, rows, C.byref(h))
+            if st:
+                _raise(st, None, ctx)
+            tabs.append(Table(ctx, h))
+        ctx.sync()  # the parts were copied out of the torch buffers
+        self.parts = self.keep = None
+        return Table.concat(tabs) if self.world > 1 else tabs[0]
+
+
+def allgather_table_async(ctx, table, dist, group=None):
+    """starts the all-gather of `table`'s rows (one size exchange + one collective for all columns) and returns a
+    handle; the caller may run other GPU work (e.g. parse its probe shard) before handle.wait()"""
+    import torch
     cols = table.columns
     n = len(table)
     ctx.sync()
@@ -93,20 +119,12 @@ def allgather_table(ctx, table, dist, group=None):
         ctx.lib.cpb_table_col_bytes(ctx.h, table.h, i, 0, n, C.byref(nb))
         segs.append(_as_tensor(po, 4 * (n + 1)))
         segs.append(_as_tensor(pd, nb.value))
-    parts = allgather_packed(segs, dist, group)  # one size exchange + one collective for all columns
-    torch.cuda.synchronize()
-    world = dist.get_world_size(group)
-    names, keep = _strs(cols)
-    tabs = []
-    for r in range(world):
-        rows = parts[r][0].numel() // 4 - 1
-        oa = (C.c_void_p * len(cols))(*[parts[r][2 * k].data_ptr() for k in range(len(cols))])
-        da = (C.c_void_p * len(cols))(*[parts[r][2 * k + 1].data_ptr() if parts[r][2 * k + 1].numel() else 0
-                                        for k in range(len(cols))])
-        h = C.c_void_p()
-        st = ctx.lib.cpb_table_from_device(ctx.h, len(cols), names, oa, da, rows, C.byref(h))
-        if st:
-            _raise(st, None, ctx)
-        tabs.append(Table(ctx, h))
-    ctx.sync()  # the parts were copied out of the torch buffers
-    return Table.concat(tabs) if world > 1 else tabs[0]
+    parts = allgather_packed(segs, dist, group)
+    ev = torch.cuda.Event()
+    ev.record()
+    return _PendingGather(ctx, cols, parts, ev, dist.get_world_size(group), (table, segs))
+
+
+def allgather_table(ctx, table, dist, group=None):
+    """every rank contributes its rows; returns the concatenation of all ranks' rows (rank order) on every rank"""
+    return allgather_table_async(ctx, table, dist, group).wait()
