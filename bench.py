@@ -49,18 +49,23 @@ def hbm_peak():
 
 
 class ClockSampler:
+    """nvidia-smi polled every 20 ms in the background; stop(t0, t1) keeps the samples whose timestamps fall inside
+    the timed region [t0, t1] (wall clock), so that it may be started early (nvidia-smi needs ~0.1 s to start)"""
+
     def __init__(self, index: int):
         self.p = None
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", f"--id={index}",
-                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--query-gpu=timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0: float | None = None, t1: float | None = None):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -68,20 +73,27 @@ class ClockSampler:
             out, _ = self.p.communicate(timeout=5)
         except Exception:
             self.p.kill(); out = ""
-        sm, mx, reasons = [], [], set()
+        rows = []
         for ln in out.splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
+            if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[3:7]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+        inside = [r for r in rows if t0 is not None and t1 is not None and t0 - 0.01 <= r[0] <= t1 + 0.01]
+        window = "timed region" if inside else "whole run (no sample fell inside the timed region)"
+        use = inside or rows
+        reasons = set()
+        for r in use:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median([r[1] for r in use]) if use else None,
+                "sm_max_mhz": max(r[2] for r in use) if use else None,
+                "reasons": sorted(reasons), "samples": len(use), "window": window}
 
 
 # ------------------------------------------------------------------ reference arm / cpu baseline (oracle port)
@@ -280,22 +292,24 @@ def main():
         return t
 
     def timed(fn, steps, warmup, sampler_dev=None):
+        sampler = ClockSampler(sampler_dev) if sampler_dev is not None else None  # polls through warm-up + timed steps
         for _ in range(warmup):
             r = fn(); del r
         ctx.sync(); torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(sampler_dev) if sampler_dev is not None else None
         ctx.stats(enable=True, reset=True)
         l0 = ctx.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.time()
         e0.record(stream)
         rows = 0
         for _ in range(steps):
             r = fn(); rows = len(r); del r
         e1.record(stream)
         ctx.sync(); torch.cuda.synchronize()
+        t_end = time.time()
         ms = e0.elapsed_time(e1)
         if world > 1:
             dist.barrier()
@@ -304,7 +318,7 @@ def main():
             ms = float(tms.item())
         stats = ctx.stats()
         ctx.stats(enable=False)
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_begin, t_end) if sampler else None
         return ms / steps, rows, stats, ctx.kernel_launches() - l0, clocks
 
     # ---------------- device-resident timing (value)

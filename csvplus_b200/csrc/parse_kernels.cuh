@@ -19,21 +19,12 @@
 #include "pred.cuh"
 #include "util.cuh"
 
-// A/B switches measured on B200 (tools/time_parse.py, 20 M rows): drawing the next tile's ticket early lengthens the
+// Variants measured on B200 and removed (tools/time_parse.py, 20 M rows): drawing the next tile's ticket early lengthens the
 // look-back distance (656 vs 720 GB/s); word-wise staging copies lose to the byte loop on short fields (510 vs 528 GB/s).
 // Also measured and rejected (40 M rows; filter / orders / all-columns GB/s, baseline 738 / 555 / 371):
 //   * one stage for all columns, owners copy their rows, direct offset stores (2 barriers per tile instead of 4 per
 //     column): 691 / 583 / 377 -- the barriers are not the cost, the byte loop is;
 //   * folding the parity verification and the any-slow vote into the block scan's barrier: 548 / 420 / 292.
-#ifndef CPB_EARLY_TICKET
-#define CPB_LATE_TICKET 1
-#endif
-#ifdef CPB_RT_KLOOP
-#define CPB_KLOOP_PRAGMA _Pragma("unroll 1")
-#else
-#define CPB_KLOOP_PRAGMA _Pragma("unroll")
-#endif
-
 namespace cpb {
 
 constexpr int TILE = 32768;
@@ -275,8 +266,7 @@ struct __align__(16) ParseSmem {
     uint64_t tile_prefix[2 + MAXSEL];
     uint32_t wtot[1 + MAXSEL][THREADS / 32];
     uint32_t wpar[THREADS / 32];
-    uint32_t lb_incl[THREADS / 32], lb_vals[THREADS / 32];
-    uint64_t lb_sum[THREADS / 32][2 + MAXSEL];
+    uint64_t col_total[2 + MAXSEL];  // last tile: grand totals (records, rows, bytes per column)
     uint32_t ticket;
     uint32_t pin;
     uint32_t nstruct, nterm;     // totals of the window
@@ -480,107 +470,12 @@ __device__ __forceinline__ bool generic_record(const ParseParams& P, const Parse
 }
 
 
-// ------------------------------------------------------------------ block-wide decoupled look-back
-// Every thread inspects one predecessor tile (256 per round) so that a whole wave of concurrently
-// running tiles is crossed in one or two L2 round trips.
+// ------------------------------------------------------------------ decoupled look-back (one warp)
+// In steady state the nearest inclusive predecessor is a few tiles back, so one 32-wide round (one L2 round trip)
+// resolves the look-back while the other warps wait at a single barrier.  (A block-wide, 256-predecessors-per-round
+// version was measured slower.)
 constexpr unsigned long long LB_AGG = 1ull << 62, LB_INCL = 2ull << 62, LB_VAL = (1ull << 62) - 1;
 
-// chain 1: parity of the quote bytes before `tile`
-__device__ __forceinline__ uint32_t lookback_parity(const uint32_t* st1, uint32_t tile, ParseSmem& sm) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t acc = 0;
-    int64_t base = (int64_t)tile - 1;
-    bool first = true;  // the nearest inclusive predecessor is usually within 32 tiles: round 0 is one warp wide
-    for (;;) {
-        const bool active = !first || warp == 0;
-        const int64_t p = base - (first ? lane : tid);
-        uint32_t s = active ? 2u : 1u;
-        if (active && p >= 0) { do { s = ld_relaxed_u32(&st1[p]); } while ((s & 3u) == 0); }
-        const uint32_t incl = __ballot_sync(0xffffffffu, (s & 3u) == 2u);
-        const uint32_t vals = __ballot_sync(0xffffffffu, (s >> 2) & 1u);
-        if (lane == 0) { sm.lb_incl[warp] = incl; sm.lb_vals[warp] = vals; }
-        __syncthreads();
-        bool found = false;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; w++) {
-            if (!found) {
-                const uint32_t im = sm.lb_incl[w], vm = sm.lb_vals[w];
-                if (im) { const int f = __ffs(im) - 1; acc ^= __popc(vm & (0xffffffffu >> (31 - f))) & 1; found = true; }
-                else acc ^= __popc(vm) & 1;
-            }
-        }
-        __syncthreads();
-        if (found) break;
-        base -= first ? 32 : THREADS;
-        first = false;
-    }
-    return acc;
-}
-
-// chain 2: exclusive prefix of the NP running totals -> sm.tile_prefix[0..NP)
-template <int KMAX>
-__device__ __forceinline__ void lookback_totals(const unsigned long long* words, uint32_t tile, int NP, ParseSmem& sm) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < NP) sm.tile_prefix[tid] = 0;
-    int64_t base = (int64_t)tile - 1;
-    bool first = true;
-    for (;;) {
-        const bool active = !first || warp == 0;
-        const int64_t p = active ? base - (first ? lane : tid) : -1;
-        unsigned long long v[KMAX + 2];
-        bool is_incl = active;
-        if (p >= 0) {
-            const unsigned long long* w = words + (uint64_t)p * NP;
-            // a tile publishes its NP words independently (aggregate first, later inclusive): re-read until
-            // all words are valid and carry the same status
-            for (;;) {
-#pragma unroll
-                for (int c = 0; c < KMAX + 2; c++) v[c] = c < NP ? ld_relaxed_u64((const uint64_t*)(w + c)) : 0ull;
-                const unsigned long long f0 = v[0] >> 62;
-                bool ok = f0 != 0;
-#pragma unroll
-                for (int c = 1; c < KMAX + 2; c++) if (c < NP) ok = ok && (v[c] >> 62) == f0;
-                if (ok) break;
-            }
-            is_incl = (v[0] >> 62) == 2;
-        } else {
-#pragma unroll
-            for (int c = 0; c < KMAX + 2; c++) v[c] = LB_INCL;  // before the first tile: inclusive zero
-        }
-        const uint32_t incl = __ballot_sync(0xffffffffu, is_incl);
-        if (lane == 0) sm.lb_incl[warp] = incl;
-        __syncthreads();
-        int wf = -1, lf = 0;
-#pragma unroll
-        for (int w = THREADS / 32 - 1; w >= 0; w--) { const uint32_t im = sm.lb_incl[w]; if (im) { wf = w; lf = __ffs(im) - 1; } }
-        const bool take = p >= 0 && (wf < 0 || warp < wf || (warp == wf && lane <= lf));
-#pragma unroll
-        for (int c = 0; c < KMAX + 2; c++) {
-            if (c < NP) {
-                uint64_t x = take ? (uint64_t)(v[c] & LB_VAL) : 0ull;
-                // an aggregate that was read while its tile was switching to inclusive is still an aggregate here:
-                // words of tiles nearer than the first inclusive tile all carry the AGG flag for word 0, and for the
-                // other words the value is taken by its own flag below
-                x = warp_sum_u64(x);
-                if (lane == 0) sm.lb_sum[warp][c] = x;
-            }
-        }
-        __syncthreads();
-        if (tid < NP) {
-            uint64_t t = 0;
-#pragma unroll
-            for (int w = 0; w < THREADS / 32; w++) t += sm.lb_sum[w][tid];
-            sm.tile_prefix[tid] += t;
-        }
-        __syncthreads();
-        if (wf >= 0) break;
-        base -= first ? 32 : THREADS;
-        first = false;
-    }
-}
-
-// ---- single-warp variants: in steady state the nearest inclusive predecessor is a few tiles back, so one
-// 32-wide round (one L2 round trip) resolves the look-back while the other warps wait at a single barrier.
 __device__ __forceinline__ uint32_t lookback_parity_w0(const uint32_t* st1, uint32_t tile) {
     const int lane = threadIdx.x & 31;
     uint32_t acc = 0;
@@ -652,19 +547,9 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
     const uint8_t* lits = lits_in_smem ? sm.lits : P.lits;
     __syncthreads();
     uint32_t phase = 0;
-    // thread 0 draws the next tile's ticket in the middle of the current tile, so the atomic's round trip is hidden
-#ifdef CPB_LATE_TICKET
-    uint32_t next_ticket = 0; (void)next_ticket;
-#else
-    uint32_t next_ticket = tid == 0 ? atomicAdd(P.ticket, 1u) : 0u;
-#endif
 
     for (;;) {
-#ifdef CPB_LATE_TICKET
         if (tid == 0) sm.ticket = atomicAdd(P.ticket, 1u);
-#else
-        if (tid == 0) sm.ticket = next_ticket;
-#endif
         __syncthreads();
         const uint32_t tile = sm.ticket;
         if (tile >= P.ntiles) break;
@@ -919,9 +804,6 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
             pin_known = true;
             if (pin) goto retry;
         }
-#ifndef CPB_LATE_TICKET
-        if (tid == 0) next_ticket = atomicAdd(P.ticket, 1u);
-#endif
         // staged output (coalesced stores) needs every row of the tile cached and on the fast path
         const bool staged_pre = !__syncthreads_or(any_slow) && flat_ok && L <= RC;
         // ---- block scan of (records | rows << 16, bytes[k])
@@ -972,12 +854,12 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
             if (tile == P.ntiles - 1 && tid < NP) {  // totals + end-of-column sentinels
                 const unsigned long long total = sm.tile_prefix[tid] + mine;
                 P.result->totals[tid] = total;
-                sm.lb_sum[0][tid] = total;
+                sm.col_total[tid] = total;
             }
             if (tile == P.ntiles - 1) {
                 __syncthreads();
-                const unsigned long long rows = sm.lb_sum[0][1];
-                if (tid >= 2 && tid < NP && rows <= P.row_cap) P.out_off[tid - 2][rows] = (uint32_t)sm.lb_sum[0][tid];
+                const unsigned long long rows = sm.col_total[1];
+                if (tid >= 2 && tid < NP && rows <= P.row_cap) P.out_off[tid - 2][rows] = (uint32_t)sm.col_total[tid];
             }
         }
 
@@ -1003,9 +885,8 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                 const uint64_t row_base = sm.tile_prefix[1];
                 const uint32_t osh = (uint32_t)(row_base & 3);
                 if (nrow != 0 && row == 0) P.result->first_row_ordinal = rec0 + first_surv_rec;
-                // (CPB_RT_KLOOP runs the column loop at run time -- one copy of the staging code instead of KMAX, the
-                // register-resident per-column values picked by select chains; measured slower: 679 vs 736 GB/s)
-                CPB_KLOOP_PRAGMA
+                // (a run-time column loop -- one copy of the staging code instead of KMAX -- measured slower: 679 vs 736 GB/s)
+#pragma unroll
                 for (int k = 0; k < KMAX; k++) {
                     if (k < (EXACT ? KMAX : P.nsel)) {
                         const uint64_t dbase = sm.tile_prefix[2 + k];
@@ -1052,15 +933,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(co
                                 const uint32_t st = ost[osh + j] - (uint32_t)dbase + r16;  // shifted tile-local start
                                 const uint32_t lo = st > c0 ? st : c0, hi = st + len < c0 + CH ? st + len : c0 + CH;
                                 const uint8_t* sp = sm.data + PRE + (f & 0xffffu) - st;
-                                // bytes up to the next aligned staging word, then whole words (source re-aligned by a funnel
-                                // shift of two aligned shared-memory words), then the tail bytes
-                                uint32_t x = lo;
-#ifdef CPB_WORD_COPY
-                                for (; x < hi && ((x - c0) & 3u); x++) stage[x - c0] = sp[x];
-                                const uint32_t sbase = PRE + (f & 0xffffu) - st;  // sm.data offset of shifted position 0 of this field
-                                for (; x + 4 <= hi; x += 4) *reinterpret_cast<uint32_t*>(stage + (x - c0)) = lds_u32_at(sm.data, sbase + x);
-#endif
-                                for (; x < hi; x++) stage[x - c0] = sp[x];
+                                for (uint32_t x = lo; x < hi; x++) stage[x - c0] = sp[x];  // (word-wise copies measured slower)
                             }
                             __syncthreads();
                             const uint32_t cend = c0 + CH < r16 + B ? c0 + CH : r16 + B;
