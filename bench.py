@@ -49,8 +49,9 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi polled every 20 ms in the background; stop(t0, t1) keeps the samples whose timestamps fall inside
-    the timed region [t0, t1] (wall clock), so that it may be started early (nvidia-smi needs ~0.1 s to start)"""
+    """nvidia-smi polled every 100 ms in the background (a 20 ms poll measurably slows the step: its NVML queries
+    contend with the launches, 21.3 -> 23.5 ms); stop(t0, t1) keeps the samples whose timestamps fall inside the
+    timed region [t0, t1] (wall clock), so that it may be started early (nvidia-smi needs ~0.1 s to start)"""
 
     def __init__(self, index: int):
         self.p = None
@@ -59,7 +60,7 @@ class ClockSampler:
                 ["nvidia-smi", f"--id={index}",
                  "--query-gpu=timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "20"],
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None

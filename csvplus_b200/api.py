@@ -394,6 +394,16 @@ class Table:
         self.ctx.lib.cpb_host_free(self.ctx.h, p)
         return out
 
+    def to_csv_device(self, *cols) -> "DeviceBuffer":
+        """ToCsv with the serialised bytes left in HBM (cpb_table_to_csv_device)"""
+        a, keep = _strs(cols); p = C.c_void_p(); n = C.c_uint64(); e = _abi.Error()
+        st = self.ctx.lib.cpb_table_to_csv_device(self.ctx.h, self.h, a, len(cols), C.byref(p), C.byref(n), C.byref(e))
+        if st:
+            _raise(st, e, self.ctx)
+        b = DeviceBuffer.__new__(DeviceBuffer)
+        b.ctx, b.nbytes, b.ptr = self.ctx, n.value, p.value
+        return b
+
     @staticmethod
     def concat(parts: list["Table"]) -> "Table":
         ctx = parts[0].ctx
