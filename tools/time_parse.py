@@ -19,3 +19,6 @@ st = run("orders", lambda: cp.parse_csv(ctx, orders, spec=[("cust_id", -1), ("pr
 s = st["csv_scan"]; print("  orders csv_scan GB/s (S_in):", orders.nbytes / (s["ms"] / s["launches"] * 1e-3) / 1e9)
 st = run("all6", lambda: cp.parse_csv(ctx, people)[0])
 s = st["csv_scan"]; print("  all6 csv_scan GB/s (S_in):", people.nbytes / (s["ms"] / s["launches"] * 1e-3) / 1e9)
+st = run("general(comment=#)", lambda: cp.parse_csv(ctx, people, spec=[("name", -1), ("surname", -1), ("id", -1)], pred=cp.Like({"name": "Amelia"}), comment="#")[0])
+tot = sum(v["ms"] for v in st.values()) / 5
+print("  general path GB/s (S_in, all kernels):", people.nbytes / (tot * 1e-3) / 1e9)
