@@ -357,8 +357,8 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
             uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
             join_probe32_kernel<<<grid, 256, 0, c->stream>>>(kd, np, ht.slots32->as<Slot32>(), ht.nslots32, lo->as<uint32_t>(), cnt->as<uint32_t>(), not_one);
         } else if (smem <= 200 * 1024) {
-            static bool configured = false;
-            if (!configured) { CPB_CUDA(cudaFuncSetAttribute(join_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+            // (per device, and cheap: set on every launch rather than cached per process)
+            CPB_CUDA(cudaFuncSetAttribute(join_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count);
             join_probe_kernel<true><<<grid, 256, smem, c->stream>>>(pimg->as<uint64_t>(), np, ix.image->as<uint64_t>(), ni, ht.pbytes,
                                                                     ht.slots->as<uint32_t>(), ht.nslots, ht.heads->as<uint32_t>(), ht.nheads,

@@ -15,6 +15,7 @@
 // gathers field bytes.  Records containing quotes (or running past the staged window) take an exact
 // sequential state machine that restates Go's readRecord byte for byte.
 #include <algorithm>
+#include <mutex>
 
 #include "core.hpp"
 #include "pred.cuh"
@@ -37,15 +38,23 @@ const char* kind_text(int k) {
 
 template <int KMAX, bool EXACT, bool HP>
 void launch_scan_hp(Ctx* c, const ParseParams& P, uint64_t algo_bytes) {
-    static bool configured = false;
+    // function attributes and occupancy are per device: cached per (kernel, device) so that one process may drive
+    // several GPUs through several contexts
+    static std::mutex mu;
+    static int occ_of[64];
     const size_t smem = sizeof(ParseSmem);
-    if (!configured) {
-        CPB_CUDA(cudaFuncSetAttribute(csv_scan_kernel<KMAX, EXACT, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    int occ;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        int& cached = occ_of[c->device & 63];
+        if (cached == 0) {
+            CPB_CUDA(cudaFuncSetAttribute(csv_scan_kernel<KMAX, EXACT, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int o = 0;
+            CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, csv_scan_kernel<KMAX, EXACT, HP>, THREADS, smem));
+            cached = o < 1 ? 1 : o;
+        }
+        occ = cached;
     }
-    int occ = 0;
-    CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, csv_scan_kernel<KMAX, EXACT, HP>, THREADS, smem));
-    if (occ < 1) occ = 1;
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count * occ, P.ntiles);
     KernelTimer kt(c, "csv_scan", algo_bytes);
     csv_scan_kernel<KMAX, EXACT, HP><<<grid, THREADS, smem, c->stream>>>(P);
