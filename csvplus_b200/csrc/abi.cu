@@ -37,6 +37,10 @@ DevBuf::DevBuf(Ctx* c, size_t bytes) : ctx(c), n(bytes) {
     cudaError_t e = cudaMallocAsync(&p, size_class(bytes), c->pool, c->stream);
     if (e != cudaSuccess) { cudaGetLastError(); throw CudaFail{e, "cudaMallocAsync", __FILE__, __LINE__}; }
 }
+DevBuf::DevBuf(Ctx* owner, Ctx* user, size_t bytes) : ctx(owner), n(bytes) {
+    cudaError_t e = cudaMallocAsync(&p, size_class(bytes), owner->pool, user->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); throw CudaFail{e, "cudaMallocAsync", __FILE__, __LINE__}; }
+}
 DevBuf::~DevBuf() {
     if (p) { cudaSetDevice(ctx->device); cudaFreeAsync(p, ctx->stream); }
 }

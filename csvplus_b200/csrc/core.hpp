@@ -48,6 +48,9 @@ std::string go_quote(const std::string& s);
 struct DevBuf {  // stream-ordered allocation owned by a ctx
     Ctx* ctx = nullptr; void* p = nullptr; size_t n = 0;
     DevBuf(Ctx* c, size_t bytes);
+    // memory of `owner`'s pool, allocated in the stream order of `user` (usable by user's kernels at once) and
+    // released on owner's stream: for structures another context builds lazily inside an object owner owns
+    DevBuf(Ctx* owner, Ctx* user, size_t bytes);
     ~DevBuf();
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -152,6 +155,7 @@ struct DeviceGuard {  // every entry point: select device, serialise on the ctx
 };
 
 inline Buf dev_alloc(Ctx* c, size_t bytes) { return std::make_shared<DevBuf>(c, bytes ? bytes : 1); }
+inline Buf dev_alloc_owned(Ctx* owner, Ctx* user, size_t bytes) { return std::make_shared<DevBuf>(owner, user, bytes ? bytes : 1); }
 
 inline std::string to_string(cpb_str s) { return std::string(s.ptr ? s.ptr : "", (size_t)s.len); }
 

@@ -441,7 +441,7 @@ static RowSlots& ensure_row_slots(Ctx* c, Index& ix, const std::vector<int>& col
         SlotCols sc{};
         sc.nc = (int)cols.size();
         for (int k = 0; k < sc.nc; k++) { sc.off[k] = t.cols[cols[k]].off(); sc.data[k] = t.cols[cols[k]].bytes(); }
-        Buf lens = dev_alloc(c, n * 4), stat = dev_alloc(c, 8);
+        Buf lens = dev_alloc_owned(ix.ctx, c, n * 4), stat = dev_alloc(c, 8);  // kept structures: the index owner's pool
         CPB_CUDA(cudaMemsetAsync(stat->p, 0, 8, c->stream));
         uint64_t col_bytes = n * 4 * sc.nc;
         {
@@ -454,7 +454,7 @@ static RowSlots& ensure_row_slots(Ctx* c, Index& ix, const std::vector<int>& col
         CPB_CUDA(cudaStreamSynchronize(c->stream));
         if (hs[1] == 0 && hs[0] <= RS_MAXS) {
             rs.S = std::max<uint32_t>(16, (hs[0] + 15) & ~15u);
-            rs.slots = dev_alloc(c, n * rs.S);
+            rs.slots = dev_alloc_owned(ix.ctx, c, n * rs.S);
             rs.lens = lens;
             KernelTimer kt(c, "slot_build", n * rs.S * 2);
             slot_fill_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sc, n, rs.S, rs.slots->as<uint8_t>());

@@ -263,7 +263,8 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
     }
     exclusive_scan_u32(c, head->as<uint32_t>(), pos->as<uint32_t>(), n, tot->as<uint64_t>());
     ht.nheads = read_u64(c, tot->p);
-    ht.heads = dev_alloc(c, (ht.nheads + 1) * 4);
+    // what stays in the index comes from the index owner's pool: the probing context may be shut down first
+    ht.heads = dev_alloc_owned(ix.ctx, c, (ht.nheads + 1) * 4);
     compact_heads_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(head->as<uint32_t>(), pos->as<uint32_t>(), ht.heads->as<uint32_t>(), n);
     uint64_t want = std::max<uint64_t>(16, ht.nheads * 2);
     ht.nslots = 1; while (ht.nslots < want) ht.nslots <<= 1;
@@ -271,7 +272,7 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
     // embedded-key 16 / 32 byte slots
     const bool large = (ht.nslots + ht.nheads + 1) * 4 > 200 * 1024;
     if (!(large && ht.pbytes <= 24)) {
-        ht.slots = dev_alloc(c, ht.nslots * 4);
+        ht.slots = dev_alloc_owned(ix.ctx, c, ht.nslots * 4);
         CPB_CUDA(cudaMemsetAsync(ht.slots->p, 0xff, ht.nslots * 4, c->stream));
         KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8));
         hash_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
@@ -281,7 +282,7 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
     const bool too_large_for_smem = (ht.nslots + ht.nheads + 1) * 4 > 200 * 1024;
     if (ht.pbytes <= 12 && ht.nheads == n && too_large_for_smem) {  // unique short keys: 16-byte slots
         ht.nslots16 = ht.nheads * 2 + 16;
-        ht.slots16 = dev_alloc(c, ht.nslots16 * sizeof(Slot16));
+        ht.slots16 = dev_alloc_owned(ix.ctx, c, ht.nslots16 * sizeof(Slot16));
         CPB_CUDA(cudaMemsetAsync(ht.slots16->p, 0, ht.nslots16 * sizeof(Slot16), c->stream));
         KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8) + ht.nslots16 * 16);
         hash16_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
@@ -289,7 +290,7 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
         CPB_CUDA(cudaGetLastError());
     } else if (ht.pbytes <= 24 && too_large_for_smem) {  // key fits a sector
         ht.nslots32 = ht.nheads + ht.nheads / 2 + 16;
-        ht.slots32 = dev_alloc(c, ht.nslots32 * sizeof(Slot32));
+        ht.slots32 = dev_alloc_owned(ix.ctx, c, ht.nslots32 * sizeof(Slot32));
         CPB_CUDA(cudaMemsetAsync(ht.slots32->p, 0, ht.nslots32 * sizeof(Slot32), c->stream));
         KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8) + ht.nslots32 * 32);
         hash32_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
