@@ -108,7 +108,12 @@ typedef struct cpb_pred {
     const struct cpb_pred* const* children;
 } cpb_pred;
 
-/* ------------------------------------------------------------------ context */
+/* ------------------------------------------------------------------ context
+ * A ctx = one device + one stream + one stream-ordered memory pool; calls on one ctx are serialised, several
+ * ctxs (one per host thread) run concurrently.  Tables and indices belong to the ctx that created them and must
+ * be freed before it is shut down.  An index may be probed (cpb_join / cpb_except) by tables of other ctxs of the
+ * same device: what such a probe builds lazily inside the index is taken from the index owner's pool, so the
+ * probing ctx may be shut down before the index; the RESULT table belongs to the probing ctx. */
 int cpb_abi_version(void);
 int cpb_init(int device, cpb_ctx** out);
 void cpb_shutdown(cpb_ctx* ctx);
