@@ -24,20 +24,29 @@
 // Also measured and rejected (40 M rows; filter / orders / all-columns GB/s, baseline 738 / 555 / 371):
 //   * one stage for all columns, owners copy their rows, direct offset stores (2 barriers per tile instead of 4 per
 //     column): 691 / 583 / 377 -- the barriers are not the cost, the byte loop is;
-//   * folding the parity verification and the any-slow vote into the block scan's barrier: 548 / 420 / 292.
+//   * folding the parity verification and the any-slow vote into the block scan's barrier: 548 / 420 / 292;
+//   * 16 KiB tiles with 128-thread CTAs (-DCPB_TILE=16384 -DCPB_THREADS=128, 6 CTAs/SM): 650 / 551 / 393 against
+//     714 / 582 / 406 for the 32 KiB / 256-thread default in the same run -- the per-tile fixed costs win.
 namespace cpb {
 
-constexpr int TILE = 32768;
+#ifndef CPB_TILE
+#define CPB_TILE 32768
+#endif
+#ifndef CPB_THREADS
+#define CPB_THREADS 256
+#endif
+constexpr int TILE = CPB_TILE;
 constexpr int PRE = 16;
 constexpr int HALO = 2048;
 constexpr int WIN = TILE + HALO;
-constexpr int THREADS = 256;
+constexpr int THREADS = CPB_THREADS;
 constexpr int WIN_WORDS = WIN / 32;        // 1088
 constexpr int TILE_WORDS = TILE / 32;      // 1024
 constexpr int HALO_WORDS = HALO / 32;      // 64
 constexpr int WPT = TILE_WORDS / THREADS;  // bitmap words per thread (4)
-constexpr int SCAP = 8192;                 // structural index capacity per window
-constexpr int LCAP = 2048;                 // terminator capacity per window
+constexpr int SCAP = TILE / 4;             // structural index capacity per window (8192)
+constexpr int LCAP = TILE / 16;            // terminator capacity per window (2048)
+static_assert(TILE_WORDS == 4 * THREADS, "every thread owns one uint4 of each bitmap");
 constexpr int LITS_SMEM = 256;
 constexpr int MAXSEL = CPB_MAX_PARSE_COLS;
 constexpr int HDR_MAX_FIELDS = 1024;
@@ -534,7 +543,7 @@ __device__ __forceinline__ void lookback_totals_w0(const unsigned long long* wor
 }
 
 template <int KMAX, bool EXACT, bool HP>
-__global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 3 : 1) csv_scan_kernel(const __grid_constant__ ParseParams P) {
+__global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_scan_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ParseSmem& sm = *reinterpret_cast<ParseSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
