@@ -177,3 +177,40 @@ def test_join_and_csv():
     assert out == b'a,b\n"x""y"," lead"\n,"p,q"\n'
     ex = orders.except_(cust, "cust_id")
     assert ex.values("oid") == [b"11"]
+
+
+# Go encoding/csv Writer golden vectors (writer_test.go `writeTests`, the default-settings subset ToCsv uses: Comma ',',
+# UseCRLF=false; go 1.23 per the reference's go.mod).  Each input record set is written through the oracle's ToCsv
+# (csvplus.go:379-406) under column names c0..cN; the expected text is the header line + Go's expected output.
+WRITER_KATS = [
+    ([["abc"]], "abc\n"),
+    ([['"abc"']], '"""abc"""\n'),
+    ([['a"b']], '"a""b"\n'),
+    ([['"a"b"']], '"""a""b"""\n'),
+    ([[" abc"]], '" abc"\n'),
+    ([["abc,def"]], '"abc,def"\n'),
+    ([["abc", "def"]], "abc,def\n"),
+    ([["abc"], ["def"]], "abc\ndef\n"),
+    ([["abc\ndef"]], '"abc\ndef"\n'),
+    ([["abc\rdef"]], '"abc\rdef"\n'),
+    ([[""]], "\n"),
+    ([["", ""]], ",\n"),
+    ([["", "", ""]], ",,\n"),
+    ([["", "", "a"]], ",,a\n"),
+    ([["", "a", ""]], ",a,\n"),
+    ([["", "a", "a"]], ",a,a\n"),
+    ([["a", "", ""]], "a,,\n"),
+    ([["a", "", "a"]], "a,,a\n"),
+    ([["a", "a", ""]], "a,a,\n"),
+    ([["a", "a", "a"]], "a,a,a\n"),
+    ([["\\."]], '"\\."\n'),
+]
+
+
+@pytest.mark.parametrize("i", range(len(WRITER_KATS)))
+def test_encoding_csv_writer_kat(i):
+    recs, want = WRITER_KATS[i]
+    names = ["c%d" % k for k in range(len(recs[0]))]
+    out, err = orc.take_rows([dict(zip(names, r)) for r in recs]).to_csv(*names)
+    assert err is None
+    assert out == (",".join(names) + "\n" + want).encode()
