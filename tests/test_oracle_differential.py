@@ -72,3 +72,47 @@ def test_oracle_index_join_match_python_restatement(seed):
     vals = [rng.choice(irows)[k] for k in kcols[:non]]
     want = [r for r in srt if [r[k] for k in kcols[:non]] == vals]
     assert oi.find(*vals).to_csv(*kcols, "v")[0] == _dump(want, kcols + ["v"])
+
+
+# ------------------------------------------------------------------ ResolveDuplicates (csvplus.go:810-867), including §Q1
+def _py_dedup(rows, cols, resolve):
+    """index-based restatement of indexImpl.dedup; resolve(group) -> row or None ("empty row": drop the group).
+    Keeps the reference's quirk: the scan for the next duplicate copies rows[lower-1] only while lower < len(rows),
+    so a trailing run of singletons loses its last row whenever at least one duplicate group was resolved."""
+    key = lambda r: [r[c] for c in cols]
+    rows = list(rows)
+    n = len(rows)
+    lower = 1
+    while lower < n and key(rows[lower - 1]) != key(rows[lower]):
+        lower += 1
+    if lower >= n:
+        return rows
+    dest = lower - 1
+    while lower < n:
+        upper = lower
+        while upper < n and key(rows[upper]) == key(rows[lower]):
+            upper += 1
+        row = resolve(rows[lower - 1: upper])
+        lower = upper + 1
+        if row is not None:
+            rows[dest] = row; dest += 1
+        while lower < n:
+            if key(rows[lower - 1]) == key(rows[lower]):
+                break
+            rows[dest] = rows[lower - 1]
+            lower += 1; dest += 1
+    return rows[:dest]
+
+
+@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("mode", ["min", "drop", "first"])
+def test_oracle_dedup_matches_python_restatement(seed, mode):
+    rng = random.Random(100 + seed)
+    rows = [{"k": rng.choice("abcdefgh"[: rng.randrange(1, 9)]), "w": "%02d" % rng.randrange(50), "n": str(i)} for i in range(rng.randrange(1, 40))]
+    oi = orc.take_rows(rows).index_on("k")
+    oi.dedup(mode, "w")
+    srt = _py_sorted(rows, ["k"])
+    resolve = {"drop": lambda g: None, "first": lambda g: g[0],
+               "min": lambda g: min(g, key=lambda r: r["w"].encode())}[mode]  # min() keeps the first of equal minima, like the oracle's strict <
+    want = _py_dedup(srt, ["k"], resolve)
+    assert oi.rows().to_csv("k", "w", "n")[0] == _dump(want, ["k", "w", "n"])
