@@ -11,7 +11,8 @@ import pytest
 from oracle import oracle as orc
 from tests.pyref_csv import Reader
 
-ALPHABET = [b"a", b"b", b",", b",", b'"', b'"', b"\n", b"\n", b"\r", b"\r\n", b" ", b"#", b"\t", b'""', b'",', b'"\n']
+ALPHABET = [b"a", b"b", b",", b",", b'"', b'"', b"\n", b"\n", b"\r", b"\r\n", b" ", b"#", b"\t", b'""', b'",', b'"\n',
+            b"\xc3\xa9", b"\xe2\x82\xac", b"\xff", b"\x00"]  # multi-byte UTF-8, an invalid byte and NUL are ordinary field bytes
 COMBOS = list(itertools.product([False, True], [False, True], ["", "#"], [0, -1, 2]))
 
 
