@@ -50,7 +50,9 @@ SYMBOLS = [
     "cpb_table_concat", "cpb_table_select", "cpb_table_drop", "cpb_table_filter", "cpb_table_slice", "cpb_table_free",
     "cpb_index_build", "cpb_index_num_rows", "cpb_index_num_keys", "cpb_index_table", "cpb_index_find", "cpb_index_sub",
     "cpb_index_dup_groups", "cpb_index_dedup_apply", "cpb_free", "cpb_index_free",
-    "cpb_join", "cpb_except", "cpb_table_to_csv", "cpb_table_to_csv_device",
+    "cpb_join", "cpb_except", "cpb_table_to_csv", "cpb_table_to_csv_device", "cpb_table_to_csv_into",
+    "cpb_comm_unique_id", "cpb_comm_init_rank", "cpb_init_multi", "cpb_comm_size", "cpb_comm_rank", "cpb_allgather_table",
+    "cpb_allgather_tables", "cpb_allgather_u64", "cpb_allgather_layout",
     "cpb_stats_enable", "cpb_stats_reset", "cpb_stats_get", "cpb_kernel_launches", "cpb_gen_csv",
 ]
 
@@ -110,6 +112,16 @@ def load():
         "cpb_except": (i32, [vp, vp, vp, P(Str), i32, P(vp), P(Error)]),
         "cpb_table_to_csv": (i32, [vp, vp, P(Str), i32, P(vp), P(u64), P(Error)]),
         "cpb_table_to_csv_device": (i32, [vp, vp, P(Str), i32, P(vp), P(u64), P(Error)]),
+        "cpb_table_to_csv_into": (i32, [vp, vp, P(Str), i32, i32, vp, u64, P(u64), P(Error)]),
+        "cpb_comm_unique_id": (i32, [vp]),
+        "cpb_comm_init_rank": (i32, [vp, i32, i32, vp]),
+        "cpb_init_multi": (i32, [P(i32), i32, P(vp)]),
+        "cpb_comm_size": (i32, [vp]),
+        "cpb_comm_rank": (i32, [vp]),
+        "cpb_allgather_table": (i32, [vp, vp, P(vp)]),
+        "cpb_allgather_tables": (i32, [P(vp), P(vp), i32, P(vp)]),
+        "cpb_allgather_u64": (i32, [vp, P(u64), i32, P(u64)]),
+        "cpb_allgather_layout": (i32, [i32, i32, P(u64), P(u64), P(u64)]),
         "cpb_stats_enable": (i32, [vp, i32]),
         "cpb_stats_reset": (i32, [vp]),
         "cpb_stats_get": (i32, [vp, P(KStat), i32, P(i32)]),

@@ -341,6 +341,19 @@ class Table:
             _raise(st, None, ctx)
         return Table(ctx, h)
 
+    @staticmethod
+    def from_device_columns(ctx: Context, names: list[str], columns: list[tuple], nrows: int) -> "Table":
+        """cpb_table_from_device: columns[k] = (device pointer of uint32 offsets[nrows+1], device pointer of the bytes);
+        the buffers are copied, so the caller may release them once the ctx has been synchronised"""
+        na, keep = _strs(names)
+        oa = (C.c_void_p * max(1, len(names)))(*[c[0] for c in columns])
+        da = (C.c_void_p * max(1, len(names)))(*[c[1] or 0 for c in columns])
+        h = C.c_void_p()
+        st = ctx.lib.cpb_table_from_device(ctx.h, len(names), na, oa, da, nrows, C.byref(h))
+        if st:
+            _raise(st, None, ctx)
+        return Table(ctx, h)
+
     # thin wrappers of the table-level ABI
     def select(self, *cols) -> "Table":
         a, keep = _strs(cols); h = C.c_void_p(); e = _abi.Error()
@@ -393,6 +406,15 @@ class Table:
         out = C.string_at(p.value, n.value)
         self.ctx.lib.cpb_host_free(self.ctx.h, p)
         return out
+
+    def to_csv_into(self, dst: "HostBuffer", offset: int, *cols, header: bool = True) -> int:
+        """one batch of a streamed ToCsv into pinned host memory (cpb_table_to_csv_into); returns the bytes written"""
+        a, keep = _strs(cols); n = C.c_uint64(); e = _abi.Error()
+        st = self.ctx.lib.cpb_table_to_csv_into(self.ctx.h, self.h, a, len(cols), int(header), C.c_void_p(dst.ptr + offset),
+                                                dst.nbytes - offset, C.byref(n), C.byref(e))
+        if st:
+            _raise(st, e, self.ctx)
+        return n.value
 
     def to_csv_device(self, *cols) -> "DeviceBuffer":
         """ToCsv with the serialised bytes left in HBM (cpb_table_to_csv_device)"""
@@ -488,6 +510,27 @@ class Index:
         if st:
             _raise(st, None, self.ctx)
         return Index(self.ctx, h, self.columns[len(values):])
+
+    def dup_groups(self):
+        """[lo, hi) sorted-row ranges of every run of >= 2 rows with equal keys (cpb_index_dup_groups) as two int64 arrays"""
+        ng = C.c_int64(); lo = C.POINTER(C.c_int64)(); hi = C.POINTER(C.c_int64)()
+        st = self.ctx.lib.cpb_index_dup_groups(self.ctx.h, self.h, C.byref(ng), C.byref(lo), C.byref(hi))
+        if st:
+            _raise(st, None, self.ctx)
+        n = ng.value
+        try:
+            a = np.ctypeslib.as_array(lo, shape=(max(n, 1),))[:n].copy()
+            b = np.ctypeslib.as_array(hi, shape=(max(n, 1),))[:n].copy()
+        finally:
+            self.ctx.lib.cpb_free(lo); self.ctx.lib.cpb_free(hi)
+        return a, b
+
+    def dedup_apply(self, keep, bug_compatible: bool = True):
+        """keep[g] = sorted position of the row kept for group g, or -1 to drop the group (cpb_index_dedup_apply)"""
+        k = np.ascontiguousarray(keep, dtype=np.int64)
+        st = self.ctx.lib.cpb_index_dedup_apply(self.ctx.h, self.h, len(k), k.ctypes.data_as(C.POINTER(C.c_int64)), int(bug_compatible))
+        if st:
+            _raise(st, None, self.ctx)
 
     def ResolveDuplicates(self, resolve: Callable[[list[Row]], Row | None], bug_compatible: bool = True):
         """csvplus.go:651-653 / dedup :810-867.  `resolve` gets each group of rows with equal keys and returns one

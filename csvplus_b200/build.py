@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libcsvplus_b200.so")
-SOURCES = ["abi.cu", "parse.cu", "parse_general.cu", "gather.cu", "sort.cu", "join.cu", "write.cu", "gen.cu"]
+SOURCES = ["abi.cu", "parse.cu", "parse_general.cu", "gather.cu", "sort.cu", "join.cu", "write.cu", "gen.cu", "comm.cu"]
 HEADERS = ["core.hpp", "util.cuh", "pred.cuh", "parse_kernels.cuh", os.path.join("..", "..", "include", "csvplus_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(out)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or not os.path.exists(LIB):
-        r = subprocess.run([NVCC, "-shared", "-cudart", "static", "-o", LIB, *objs], capture_output=True, text=True)
+        r = subprocess.run([NVCC, "-shared", "-cudart", "static", "-o", LIB, *objs, "-ldl"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB

@@ -42,7 +42,7 @@ DevBuf::DevBuf(Ctx* owner, Ctx* user, size_t bytes) : ctx(owner), n(bytes) {
     if (e != cudaSuccess) { cudaGetLastError(); throw CudaFail{e, "cudaMallocAsync", __FILE__, __LINE__}; }
 }
 DevBuf::~DevBuf() {
-    if (p) { cudaSetDevice(ctx->device); cudaFreeAsync(p, ctx->stream); }
+    if (p && ctx) { cudaSetDevice(ctx->device); cudaFreeAsync(p, ctx->stream); }
 }
 
 void* Ctx::pinned_scratch(size_t n) {
@@ -174,6 +174,7 @@ void cpb_shutdown(cpb_ctx* h) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->drain_events();
+    cpb_comm_release(c);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaStreamDestroy(c->stream);
     if (c->own_pool) cudaMemPoolDestroy(c->pool);
@@ -354,21 +355,16 @@ int cpb_table_from_device(cpb_ctx* h, int ncols, const cpb_str* names, const uin
                           const uint8_t* const* data, int64_t nrows, cpb_table** out) {
     Ctx* c = &h->c; DeviceGuard g(c);
     CPB_TRY(c, nullptr)
-    auto t = std::make_shared<Table>(); t->ctx = c; t->nrows = nrows;
+    // the caller's arrays are wrapped without ownership and copied by the concat path, which rebases offsets that do not
+    // start at 0 (row-range views exported by cpb_table_column_device) and reads all extents with one host round trip
+    Table view; view.ctx = c; view.nrows = nrows;
     for (int i = 0; i < ncols; i++) {
         Column col; col.name = to_string(names[i]);
-        uint32_t ends[2];
-        CPB_CUDA(cudaMemcpyAsync(&ends[0], offsets[i], 4, cudaMemcpyDeviceToHost, c->stream));
-        CPB_CUDA(cudaMemcpyAsync(&ends[1], offsets[i] + nrows, 4, cudaMemcpyDeviceToHost, c->stream));
-        CPB_CUDA(cudaStreamSynchronize(c->stream));
-        if (ends[0] != 0) throw ArgError{CPB_ERR_ARG, "imported offsets must start at 0"};
-        col.offsets = dev_alloc(c, ((size_t)nrows + 1) * 4);
-        CPB_CUDA(cudaMemcpyAsync(col.offsets->p, offsets[i], ((size_t)nrows + 1) * 4, cudaMemcpyDeviceToDevice, c->stream));
-        col.data = dev_alloc(c, (size_t)ends[1] + 16);
-        if (ends[1]) CPB_CUDA(cudaMemcpyAsync(col.data->p, data[i], ends[1], cudaMemcpyDeviceToDevice, c->stream));
-        t->cols.push_back(col);
+        col.offsets = std::make_shared<DevBuf>(DevBuf::Borrow{}, offsets[i], ((size_t)nrows + 1) * 4);
+        col.data = std::make_shared<DevBuf>(DevBuf::Borrow{}, data[i], 0);
+        view.cols.push_back(col);
     }
-    *out = wrap(t);
+    *out = wrap(concat_tables(c, {&view}));
     return CPB_OK;
     CPB_CATCH(c, nullptr)
 }
@@ -378,13 +374,13 @@ int cpb_table_select(cpb_ctx* h, const cpb_table* t, const cpb_str* cols, int n,
     clear_error(err);
     CPB_TRY(c, err)
     if (n <= 0) throw ArgError{CPB_ERR_ARG, "no columns specified in SelectColumns()"};  // csvplus.go:512-514
-    auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = t->t->nrows;
+    auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = t->t->nrows; r->first_line = t->t->first_line;
     for (int i = 0; i < n; i++) {
         std::string nm = to_string(cols[i]);
         int k = t->t->find(nm);
         if (k < 0) {
             if (t->t->nrows == 0) { *out = wrap(r); r->cols.clear(); return CPB_OK; }  // no rows => Row.Select never runs
-            throw DataError{CPB_E_MISSING_COLUMN, i, 0, true, "missing column " + go_quote(nm)};  // csvplus.go:129
+            throw DataError{CPB_E_MISSING_COLUMN, i, t->t->first_line, true, "missing column " + go_quote(nm)};  // csvplus.go:129
         }
         bool dup = false;
         for (auto& cc : r->cols) if (cc.name == nm) dup = true;  // a Go map holds a name once
@@ -400,7 +396,7 @@ int cpb_table_drop(cpb_ctx* h, const cpb_table* t, const cpb_str* cols, int n, c
     CPB_TRY(c, nullptr)
     if (n <= 0) throw ArgError{CPB_ERR_ARG, "no columns specified in DropColumns()"};  // csvplus.go:494-496
     auto names = str_list(cols, n);
-    auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = t->t->nrows;
+    auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = t->t->nrows; r->first_line = t->t->first_line;
     for (auto& col : t->t->cols)
         if (std::find(names.begin(), names.end(), col.name) == names.end()) r->cols.push_back(col);
     *out = wrap(r);
@@ -415,7 +411,7 @@ int cpb_table_slice(cpb_ctx* h, const cpb_table* t, int64_t lo, int64_t hi, cpb_
     if (lo < 0) lo = 0;
     if (hi > T.nrows) hi = T.nrows;
     if (hi < lo) hi = lo;
-    auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = hi - lo;
+    auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = hi - lo; r->first_line = T.first_line + (uint64_t)lo;
     for (auto col : T.cols) { col.row0 += lo; r->cols.push_back(col); }
     *out = wrap(r);
     return CPB_OK;
@@ -564,11 +560,12 @@ static int to_csv_common(cpb_ctx* h, const cpb_table* t, const cpb_str* cols, in
     std::vector<int> idx;
     for (int i = 0; i < n; i++) {
         int k = t->t->find(names[i]);
-        if (k < 0 && t->t->nrows > 0) throw DataError{CPB_E_MISSING_COLUMN, i, 0, true, "missing column " + go_quote(names[i])};  // :392, :145
+        if (k < 0 && t->t->nrows > 0)
+            throw DataError{CPB_E_MISSING_COLUMN, i, t->t->first_line, true, "missing column " + go_quote(names[i])};  // :392, :145
         idx.push_back(k);
     }
     uint64_t total = 0;
-    Buf out = table_to_csv(c, *t->t, idx, names, &total);
+    Buf out = table_to_csv(c, *t->t, idx, names, &total, nullptr);
     *nbytes = total;
     if (to_host) {
         void* hp = nullptr;
@@ -582,6 +579,36 @@ static int to_csv_common(cpb_ctx* h, const cpb_table* t, const cpb_str* cols, in
         if (total) CPB_CUDA(cudaMemcpyAsync(dp, out->p, total, cudaMemcpyDeviceToDevice, c->stream));
         *bytes = dp;
     }
+    return CPB_OK;
+    CPB_CATCH(c, err)
+}
+// ToCsv of one batch of a streamed result into caller-owned (ideally pinned) host memory: no allocation per call,
+// the header line only when asked for (a csv.Writer writes it once, before the first batch: csvplus.go:387).
+int cpb_table_to_csv_into(cpb_ctx* h, const cpb_table* t, const cpb_str* cols, int n, int with_header, void* host_dst,
+                          uint64_t cap, uint64_t* nbytes, cpb_error* err) {
+    if (!h || !t || !nbytes || (cap && !host_dst)) return CPB_ERR_ARG;
+    Ctx* c = &h->c; DeviceGuard g(c);
+    clear_error(err);
+    CPB_TRY(c, err)
+    if (n <= 0) throw ArgError{CPB_ERR_ARG, "empty column list in ToCsv() function"};  // csvplus.go:380-382
+    auto names = str_list(cols, n);
+    std::vector<int> idx;
+    for (int i = 0; i < n; i++) {
+        int k = t->t->find(names[i]);
+        if (k < 0 && t->t->nrows > 0)
+            throw DataError{CPB_E_MISSING_COLUMN, i, t->t->first_line, true, "missing column " + go_quote(names[i])};  // :392, :145
+        idx.push_back(k);
+    }
+    uint64_t total = 0, hdr = 0;
+    Buf out = table_to_csv(c, *t->t, idx, names, &total, &hdr);
+    const uint64_t skip = with_header ? 0 : hdr;
+    *nbytes = total - skip;
+    if (*nbytes > cap) throw ArgError{CPB_ERR_ARG, "ToCsv destination too small"};
+    if (*nbytes) {
+        KernelTimer kt(c, "d2h_output", *nbytes, 0);
+        CPB_CUDA(cudaMemcpyAsync(host_dst, out->as<uint8_t>() + skip, *nbytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
     return CPB_OK;
     CPB_CATCH(c, err)
 }

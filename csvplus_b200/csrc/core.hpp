@@ -51,6 +51,8 @@ struct DevBuf {  // stream-ordered allocation owned by a ctx
     // memory of `owner`'s pool, allocated in the stream order of `user` (usable by user's kernels at once) and
     // released on owner's stream: for structures another context builds lazily inside an object owner owns
     DevBuf(Ctx* owner, Ctx* user, size_t bytes);
+    struct Borrow {};
+    DevBuf(Borrow, const void* ptr, size_t bytes) : ctx(nullptr), p(const_cast<void*>(ptr)), n(bytes) {}  // caller-owned memory: never freed here
     ~DevBuf();
     DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -137,6 +139,10 @@ struct Ctx {
     uint64_t launches = 0;
     // small pinned scratch for D2H of results
     void* pinned = nullptr; size_t pinned_n = 0;
+    // multi-GPU (comm.cu): ncclComm_t of this rank, null for a single-GPU ctx
+    void* comm = nullptr; int nranks = 1, rank = 0; bool comm_owned = false;
+    // host synchronisations this ctx has issued (cudaStreamSynchronize on its stream): a pipeline step should need few
+    uint64_t host_syncs = 0;
 
     void* pinned_scratch(size_t n);
     void drain_events();
@@ -201,9 +207,11 @@ void index_dup_groups(Ctx* c, Index& ix, std::vector<int64_t>& lo, std::vector<i
 void index_dedup_apply(Ctx* c, Index& ix, const std::vector<int64_t>& keep, bool bug_compatible);
 // write.cu
 Buf table_to_csv(Ctx* c, const Table& t, const std::vector<int>& cols, const std::vector<std::string>& names,
-                 uint64_t* nbytes);
+                 uint64_t* nbytes, uint64_t* header_bytes);
 
 }  // namespace cpb
+
+extern "C" void cpb_comm_release(cpb::Ctx* c);  // comm.cu
 
 // opaque handle layouts of the C ABI
 struct cpb_ctx { cpb::Ctx c; };

@@ -4,12 +4,13 @@
 //   classify   SWAR compares -> newline bitmap T and structural bitmap S (delimiter | newline)
 //   quotes     tiles holding a quote (or entered inside one) build the exact quote bitmap, carry the
 //              parity across tiles (look-back chain 1) and clear T inside quoted regions
-//   index      the set bits of S are expanded, in order, into a flat shared-memory array of byte
-//              positions (sidx); the structural ordinal of every terminator goes to `ord`.
-//              Line i then spans structurals (ord[i-1], ord[i]] and field j of it is found in O(1):
-//              [sidx[ord[i-1]+j]+1, sidx[ord[i-1]+j+1])  — no per-record searching, no divergence.
-//   pass 1     one thread per line (blocked): field extents of the selected columns, Like terms,
-//              field-count check -> (records, rows, bytes per column)
+//   lines      the set bits of T are expanded, in order, into `lend` (byte position of every terminator): line i
+//              spans (lend[i-1], lend[i]].  (Round 1 also expanded every structural into a flat index; the
+//              expansion cost more instructions than the field walk below saves look-ups.)
+//   pass 1     one thread per line (blocked): walks the line's structural bits of S up to its last selected
+//              field (lines of one file have the same shape, so the lanes of a warp iterate in step), the
+//              remaining delimiters are counted with popcounts -> field extents of the selected columns, Like
+//              terms, field-count check -> (records, rows, bytes per column)
 //   scan       block scan + decoupled look-back (chain 2) -> global output positions
 //   pass 2     offsets written, field bytes gathered into the column buffers
 // Lines containing quotes, or running past the window, go through the exact sequential state machine.
@@ -268,8 +269,8 @@ struct __align__(16) ParseSmem {
     uint32_t Tb[WIN_WORDS + 4];  // record terminators: '\n' outside quotes (+ a virtual one at EOF)
     uint32_t Sb[WIN_WORDS + 4];  // structural bytes: delimiter | terminator
     uint32_t Qb[WIN_WORDS + 4];  // quote bytes (exact; only built for tiles that contain quotes)
-    uint16_t sidx[SCAP];         // byte position of every structural, in order
-    uint16_t ord[LCAP];          // structural ordinal of every terminator, in order
+    uint16_t lend[LCAP + 4];     // byte position of every terminator of the window, in order
+    uint8_t stage_pad[SCAP * 2 + LCAP * 2 - (LCAP + 4) * 2];  // pass 2 stages output over Tb..stage_pad
     __align__(16) uint8_t lits[LITS_SMEM + 16];  // Like literals (word-wise compares read up to 7 bytes past the end)
     uint64_t mbar;
     uint64_t tile_prefix[2 + MAXSEL];
@@ -278,7 +279,8 @@ struct __align__(16) ParseSmem {
     uint64_t col_total[2 + MAXSEL];  // last tile: grand totals (records, rows, bytes per column)
     uint32_t ticket;
     uint32_t pin;
-    uint32_t nstruct, nterm;     // totals of the window
+    uint32_t nterm;              // terminators of the window that matter: those of the tile + the first of the halo
+    int32_t halo_term;           // position of the first terminator in the halo, -1 if none
 };
 
 __device__ __forceinline__ int next_set(const uint32_t* bm, int from, int lim) {
@@ -413,19 +415,18 @@ __device__ __forceinline__ void run_slow(const ParseParams& P, const ByteSrc& sr
     for (int k = 0; k < KMAX; k++) r.f[k] = k < (EXACT ? KMAX : P.nsel) ? so.ulen[k] : 0;
 }
 
-// Line `i` of the window through the flat structural index.  Returns false when it is not a record.
+// Line `i` of the window: (lend[i-1], lend[i]].  Returns false when it is not a record.
 template <int KMAX, bool EXACT, bool HP>
-__device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem& sm, const ByteSrc& src, const uint8_t* lits,
+__device__ __forceinline__ bool walk_line(const ParseParams& P, const ParseSmem& sm, const ByteSrc& src, const uint8_t* lits,
                                           bool lits_in_smem, uint64_t tile_base, int i, int nterm, int rel_n, int64_t rel_ds, bool tile_has_q,
                                           Rec<KMAX>& r) {
-    const int a = i == 0 ? -1 : (int)sm.ord[i - 1];
-    const int start = i == 0 ? 0 : (int)sm.sidx[a] + 1;
+    const int start = i == 0 ? 0 : (int)sm.lend[i - 1] + 1;
     if (start >= rel_n || start < rel_ds) return false;
     r.present = 0; r.eq = 0; r.err = K_OK; r.err_slot = 0; r.slow = false;
     bool to_slow = i >= nterm;  // no terminator inside the window: runs past it
-    int b = 0, e_nl = 0, e = 0;
+    int e_nl = 0, e = 0;
     if (!to_slow) {
-        b = sm.ord[i]; e_nl = sm.sidx[b];
+        e_nl = sm.lend[i];
         e = e_nl;
         if (e > start && sm.data[PRE + e - 1] == '\r') e--;  // \r\n -> \n ; trailing \r before EOF
         if (e == start) return false;                          // empty line: not a record
@@ -434,31 +435,56 @@ __device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem&
     if (to_slow) {
         run_slow<KMAX, EXACT>(P, src, tile_base + start, r);
     } else {
-        const int nf = b - a;
-        r.nf = nf;
+        // the structurals of the line, in order: delimiters, then the terminator at e_nl (always a bit of S)
+        int w = start >> 5;
+        uint32_t m = sm.Sb[w] & (0xffffffffu << (start & 31));
+        int fbeg = start, f = 0;  // field f is the one in progress, it starts at fbeg
+        bool eol = false;         // field f ended at the terminator
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) r.f[k] = 0;
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
-            r.f[k] = 0;
-            if (k < (EXACT ? KMAX : P.nsel)) {
+            if (k < (EXACT ? KMAX : P.nsel) && !eol) {
                 const int target = P.sel_field[k];
-                if (target < nf) {
-                    const int fb = target == 0 ? start : (int)sm.sidx[a + target] + 1;
-                    const int fe = target + 1 < nf ? (int)sm.sidx[a + target + 1] : e;
-                    const uint32_t len = (uint32_t)(fe - fb);
-                    r.f[k] = (uint32_t)fb | (len << 16);
+                while (f < target) {  // skip the fields before the next selected one
+                    while (m == 0) m = sm.Sb[++w];
+                    const int p = (w << 5) + __ffs(m) - 1; m &= m - 1;
+                    if (p >= e_nl) { eol = true; break; }
+                    fbeg = p + 1; f++;
+                }
+                if (!eol) {
+                    while (m == 0) m = sm.Sb[++w];
+                    const int p = (w << 5) + __ffs(m) - 1; m &= m - 1;
+                    const bool last = p >= e_nl;
+                    const uint32_t len = (uint32_t)((last ? e : p) - fbeg);
+                    r.f[k] = (uint32_t)fbeg | (len << 16);
                     r.present |= 1u << k;
                     uint32_t tm = HP ? P.slot_terms[k] : 0u;
                     while (tm) {
                         int t = __ffs(tm) - 1; tm &= tm - 1;
                         if (len == P.pred.term_len[t]) {
-                            const bool eq = lits_in_smem ? field_eq_smem(sm.data, PRE + fb, sm.lits, P.pred.term_off[t], len)
-                                                         : bytes_eq(sm.data + PRE + fb, lits + P.pred.term_off[t], len);
+                            const bool eq = lits_in_smem ? field_eq_smem(sm.data, PRE + fbeg, sm.lits, P.pred.term_off[t], len)
+                                                         : bytes_eq(sm.data + PRE + fbeg, lits + P.pred.term_off[t], len);
                             if (eq) r.eq |= 1u << t;  // (inline: an out-of-line compare measured 708 vs 729 GB/s)
                         }
                     }
+                    if (last) eol = true; else { fbeg = p + 1; f++; }
                 }
             }
         }
+        // field count = index of the last field + 1: the delimiters not walked are counted, not visited
+        int nf = f + 1;
+        if (!eol && P.expect_fields > 0) {
+            const int we = e_nl >> 5;
+            const uint32_t em = (1u << (e_nl & 31)) - 1u;
+            if (w == we) nf += __popc(m & em);
+            else {
+                nf += __popc(m);
+                for (int ww = w + 1; ww < we; ww++) nf += __popc(sm.Sb[ww]);
+                nf += __popc(sm.Sb[we] & em);
+            }
+        }
+        r.nf = nf;
     }
     finish_record<KMAX, EXACT, HP>(P, r);
     return true;
@@ -653,66 +679,48 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
         if (eof_in_win && tid == 0) { sm.Tb[rel_n >> 5] |= 1u << (rel_n & 31); sm.Sb[rel_n >> 5] |= 1u << (rel_n & 31); }
         if (eof_in_win) __syncthreads();
 
-        // ---- flat structural index
+        // ---- line ends: the terminators of the tile, in order, + the first one of the halo
         uint4 tw = reinterpret_cast<const uint4*>(sm.Tb)[tid];
         {
-            const uint4 sw = reinterpret_cast<const uint4*>(sm.Sb)[tid];
-            const uint32_t tws[4] = {tw.x, tw.y, tw.z, tw.w}, sws[4] = {sw.x, sw.y, sw.z, sw.w};
-            uint32_t cs = __popc(sw.x) + __popc(sw.y) + __popc(sw.z) + __popc(sw.w);
-            uint32_t ct = __popc(tw.x) + __popc(tw.y) + __popc(tw.z) + __popc(tw.w);
-            uint32_t v = cs | (ct << 16);
-            uint32_t inc = warp_incl_scan(v);
+            const uint32_t tws[4] = {tw.x, tw.y, tw.z, tw.w};
+            const uint32_t ct = __popc(tw.x) + __popc(tw.y) + __popc(tw.z) + __popc(tw.w);
+            const uint32_t inc = warp_incl_scan(ct);
             if (lane == 31) sm.wtot[0][warp] = inc;
-            // the 64 halo words: one per thread of warps 0-1
-            uint32_t hs = 0, ht = 0, hv = 0, hinc = 0;
-            if (tid < HALO_WORDS) { hs = sm.Sb[TILE_WORDS + tid]; ht = sm.Tb[TILE_WORDS + tid]; hv = __popc(hs) | (__popc(ht) << 16); }
-            if (warp < HALO_WORDS / 32) { hinc = warp_incl_scan(hv); if (lane == 31) sm.wtot[1][warp] = hinc; }
+            if (warp == 0) {  // 64 halo words: the line that starts last in the tile ends at the first terminator there
+                const uint32_t h0 = sm.Tb[TILE_WORDS + lane], h1 = sm.Tb[TILE_WORDS + 32 + lane];
+                const uint32_t b0 = __ballot_sync(0xffffffffu, h0 != 0), b1 = __ballot_sync(0xffffffffu, h1 != 0);
+                int pos = -1;
+                if (b0) { const int l = __ffs(b0) - 1; pos = (TILE_WORDS + l) * 32 + __ffs(__shfl_sync(0xffffffffu, h0, l)) - 1; }
+                else if (b1) { const int l = __ffs(b1) - 1; pos = (TILE_WORDS + 32 + l) * 32 + __ffs(__shfl_sync(0xffffffffu, h1, l)) - 1; }
+                if (lane == 0) sm.halo_term = pos;
+            }
             __syncthreads();
-            uint32_t ex = inc - v, tile_tot = 0;
+            uint32_t tc = inc - ct, tile_tot = 0;
 #pragma unroll
-            for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) ex += t; tile_tot += t; }
-            uint32_t o = ex & 0xffffu, tc = ex >> 16;
-            uint32_t halo_tot = 0;
-            for (int i = 0; i < HALO_WORDS / 32; i++) halo_tot += sm.wtot[1][i];
-            // the totals are known before the expansion: a window that does not fit skips it (dense fallback), one
-            // that fits needs no bounds checks
-            const bool fits = (tile_tot & 0xffffu) + (halo_tot & 0xffffu) <= (uint32_t)SCAP && (tile_tot >> 16) + (halo_tot >> 16) <= (uint32_t)LCAP;
+            for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) tc += t; tile_tot += t; }
+            // the total is known before the expansion: a window with more lines than `lend` holds skips it (dense fallback)
+            const bool fits = tile_tot + 1 <= (uint32_t)LCAP;
             if (fits) {
 #pragma unroll
                 for (int j = 0; j < WPT; j++) {
-                    uint32_t m = sws[j];
-                    const int pos0 = (tid * WPT + j) * 32;
                     uint32_t tm = tws[j];
-                    while (tm) {  // terminators are ~7x sparser than structurals: their ordinals come from a popcount
-                        int bpos = __ffs(tm) - 1; tm &= tm - 1;
-                        sm.ord[tc++] = (uint16_t)(o + __popc(m & ((1u << bpos) - 1)));
-                    }
-                    while (m) {
-                        int bpos = __ffs(m) - 1; m &= m - 1;
-                        sm.sidx[o++] = (uint16_t)(pos0 + bpos);
+                    const int pos0 = (tid * WPT + j) * 32;
+                    while (tm) {
+                        const int bpos = __ffs(tm) - 1; tm &= tm - 1;
+                        sm.lend[tc++] = (uint16_t)(pos0 + bpos);
                     }
                 }
             }
-            if (fits && tid < HALO_WORDS) {
-                uint32_t hex = hinc - hv;
-                for (int i = 0; i < warp; i++) hex += sm.wtot[1][i];
-                uint32_t o2 = (tile_tot & 0xffffu) + (hex & 0xffffu), tc2 = (tile_tot >> 16) + (hex >> 16);
-                uint32_t m = hs;
-                const int pos0 = (TILE_WORDS + tid) * 32;
-                while (m) {
-                    int bpos = __ffs(m) - 1; m &= m - 1;
-                    sm.sidx[o2] = (uint16_t)(pos0 + bpos);
-                    if ((ht >> bpos) & 1) sm.ord[tc2++] = (uint16_t)o2;
-                    o2++;
-                }
+            if (tid == 0) {
+                const int ht = sm.halo_term;
+                if (fits && ht >= 0) sm.lend[tile_tot] = (uint16_t)ht;
+                sm.nterm = fits ? tile_tot + (ht >= 0 ? 1u : 0u) : (uint32_t)LCAP + 1u;
+                sm.wpar[0] = tile_tot;  // terminators of the tile proper (needed below)
             }
-            if (tid == 0) { sm.nstruct = (tile_tot & 0xffffu) + (halo_tot & 0xffffu); sm.nterm = (tile_tot >> 16) + (halo_tot >> 16); }
-            // terminators of the tile proper (tile_tot >> 16) are needed below: stash in wpar[0]
-            if (tid == 0) sm.wpar[0] = tile_tot >> 16;
             __syncthreads();
         }
         const int nterm = (int)sm.nterm;
-        const bool flat_ok = sm.nstruct <= SCAP && sm.nterm <= LCAP;
+        const bool flat_ok = sm.nterm <= LCAP;
         const bool first_owned = tile_base == 0 || (sm.data[PRE - 1] == '\n' && pin == 0);
         // lines 1..m start inside the tile proper (terminator i-1 at position <= TILE-2); line 0 iff first_owned
         const int m_last = (int)sm.wpar[0] - (int)((sm.Tb[TILE_WORDS - 1] >> 31) & 1);
@@ -775,7 +783,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
                 const int i = i0 + tid * L + q;
                 if (q < L && i <= m_last) {
                     Rec<KMAX> r;
-                    if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
+                    if (walk_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
                         const bool surv = account(r);
                         if (r.slow) any_slow = true;
                         else if (surv) {
@@ -790,7 +798,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
                 const int i = i0 + tid * L + q;
                 if (i > m_last) break;
                 Rec<KMAX> r;
-                if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
+                if (walk_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
             }
         } else {
 #pragma unroll 1
@@ -882,7 +890,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
                 atomicMin(&P.result->err_rows, (unsigned long long)(row + err_rows_local));
             }
             if (staged) {
-                // Tb|Sb|Qb|sidx|ord are dead once pass 1 has cached every row: their 33 KB hold, per column, the
+                // Tb|Sb|Qb|lend|stage_pad are dead once pass 1 has cached every row: their 33 KB hold, per column, the
                 // row list (source extent, destination offset) and a staging buffer, so that rows are copied by
                 // all threads evenly and HBM sees full, aligned 16-byte stores.
                 uint32_t* ost = reinterpret_cast<uint32_t*>(sm.Tb);  // [LCAP + 4] destination offsets of the tile's rows
@@ -998,8 +1006,8 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
                         const int i = i0 + tid * L + q;
                         if (i > m_last) break;
                         Rec<KMAX> r;
-                        if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
-                            emit(r, tile_base + (i == 0 ? 0 : (uint64_t)sm.sidx[sm.ord[i - 1]] + 1));
+                        if (walk_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
+                            emit(r, tile_base + (i == 0 ? 0 : (uint64_t)sm.lend[i - 1] + 1));
                     }
                 } else {
 #pragma unroll 1

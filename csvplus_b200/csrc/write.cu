@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32) csv_row_write_kernel(WriteCols 
     }
 }
 
-Buf table_to_csv(Ctx* c, const Table& t, const std::vector<int>& cols, const std::vector<std::string>& names, uint64_t* nbytes) {
+Buf table_to_csv(Ctx* c, const Table& t, const std::vector<int>& cols, const std::vector<std::string>& names, uint64_t* nbytes,
+                 uint64_t* header_bytes) {
     if ((int)cols.size() > MAXW) throw ArgError{CPB_ERR_UNSUPPORTED, "more than 64 columns in ToCsv"};
     // header line (csvplus.go:387): the caller's column names through the same quoting rule
     std::string header;
@@ -140,6 +141,7 @@ Buf table_to_csv(Ctx* c, const Table& t, const std::vector<int>& cols, const std
         CPB_CUDA(cudaGetLastError());
     }
     *nbytes = header.size() + body;
+    if (header_bytes) *header_bytes = header.size();
     return out;
 }
 

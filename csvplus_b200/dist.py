@@ -10,6 +10,48 @@ from __future__ import annotations
 import ctypes as C
 
 
+def init_comm(ctx, dist, group=None) -> None:
+    """gives `ctx` the library's own NCCL communicator (cpb_comm_init_rank): rank 0 draws the unique id and
+    torch.distributed — any backend, it only carries 128 bytes — hands it to the other ranks"""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        st = ctx.lib.cpb_comm_unique_id(buf)
+        if st:
+            raise RuntimeError(f"cpb_comm_unique_id failed with status {st}")
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    raw = (C.c_uint8 * 128).from_buffer_copy(box[0])
+    st = ctx.lib.cpb_comm_init_rank(ctx.h, world, rank, raw)
+    if st:
+        from .api import _raise
+        _raise(st, None, ctx)
+
+
+def allgather_table_nccl(ctx, table):
+    """cpb_allgather_table: the library's all-gather-v of every column over its own communicator, straight into the
+    concatenated table (one host sync for the sizes); collective over the ranks of init_comm / cpb_init_multi"""
+    from .api import Table, _raise
+    h = C.c_void_p()
+    st = ctx.lib.cpb_allgather_table(ctx.h, table.h, C.byref(h))
+    if st:
+        _raise(st, None, ctx)
+    return Table(ctx, h)
+
+
+def allgather_layout(lib, meta, ncols: int):
+    """cpb_allgather_layout (pure host arithmetic): meta = per rank [rows, first_0, end_0, first_1, end_1, ...] ->
+    (row_base[nranks+1], byte_base[ncols][nranks+1])"""
+    import numpy as np
+    m = np.ascontiguousarray(meta, dtype=np.uint64)
+    nranks = m.shape[0]
+    rb = np.zeros(nranks + 1, np.uint64); bb = np.zeros((max(ncols, 1), nranks + 1), np.uint64)
+    U = C.POINTER(C.c_uint64)
+    st = lib.cpb_allgather_layout(nranks, ncols, m.ctypes.data_as(U), rb.ctypes.data_as(U), bb.ctypes.data_as(U))
+    assert st == 0
+    return rb, bb[:ncols]
+
+
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     """contiguous row range of `rank` (row-range data parallelism; concatenation in rank order = input order)"""
     return rank * total // world, (rank + 1) * total // world

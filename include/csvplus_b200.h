@@ -214,6 +214,39 @@ int cpb_table_to_csv(cpb_ctx* ctx, const cpb_table* t, const cpb_str* cols, int 
 int cpb_table_to_csv_device(cpb_ctx* ctx, const cpb_table* t, const cpb_str* cols, int n, void** dev_bytes,
                             uint64_t* nbytes, cpb_error* err);
 
+/* one batch of a streamed ToCsv/ToCsvFile (csvplus.go:379-443) into caller-owned (pinned) host memory: the header
+ * line is written only when with_header != 0 (the csv.Writer writes it once, before the first batch, :387);
+ * nothing is allocated per call, the device->host copy runs on the ctx stream and the call returns when it is done. */
+int cpb_table_to_csv_into(cpb_ctx* ctx, const cpb_table* t, const cpb_str* cols, int n, int with_header, void* host_dst,
+                          uint64_t cap, uint64_t* nbytes, cpb_error* err);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * The probe stream shards by row range with no data-path collective; the one exchange step is the all-gather of the
+ * build-side columns (each rank parses 1/N of the build file) so that every rank can build the full Index
+ * (csvplus.go:707-767) — the reference has no counterpart, it is single-threaded (csvplus.go:33-46).  Transport: NCCL
+ * over NVLink, bound at run time (libnccl.so.2).
+ *   one process per GPU : rank 0 calls cpb_comm_unique_id, the host distributes the 128 bytes (any side channel), every
+ *                         rank calls cpb_comm_init_rank on its own ctx; cpb_allgather_table is then a collective.
+ *   one process, n GPUs : cpb_init_multi creates n ctxs sharing one communicator (a Go program would use this form);
+ *                         cpb_allgather_tables drives all ranks from one thread, or cpb_allgather_table is called
+ *                         from one host thread per ctx.
+ * cpb_allgather_table returns on every rank the concatenation of all ranks' rows in rank order (= input order of
+ * row-range shards).  Row-range views are accepted.  One host synchronisation (the sizes).
+ * cpb_allgather_u64 exchanges `count` host values per rank (byte-range shards of one file exchange their quote parity
+ * and record counts with it, see cpb_parse_csv_shard); without a communicator it copies in to out. */
+#define CPB_UNIQUE_ID_BYTES 128
+int cpb_comm_unique_id(uint8_t* id128);
+int cpb_comm_init_rank(cpb_ctx* ctx, int nranks, int rank, const uint8_t* id128);
+int cpb_init_multi(const int* devices, int n, cpb_ctx** out /* [n] */);
+int cpb_comm_size(cpb_ctx* ctx);
+int cpb_comm_rank(cpb_ctx* ctx);
+int cpb_allgather_table(cpb_ctx* ctx, const cpb_table* local, cpb_table** out);
+int cpb_allgather_tables(cpb_ctx* const* ctxs, const cpb_table* const* locals, int n, cpb_table** outs /* [n] */);
+int cpb_allgather_u64(cpb_ctx* ctx, const uint64_t* in, int count, uint64_t* out /* [nranks * count] */);
+/* layout arithmetic of the all-gather-v alone (pure host code): meta[q] = {rows, (first, end) byte offset per column}
+ * of rank q -> row_base[nranks+1], byte_base[ncols][nranks+1] */
+int cpb_allgather_layout(int nranks, int ncols, const uint64_t* meta, uint64_t* row_base, uint64_t* byte_base);
+
 /* ------------------------------------------------------------------ measurement
  * Per-kernel launch records of this ctx since the last reset: name, launches, device ms (CUDA events on
  * the ctx stream) and algorithmic bytes, for the roofline JSON of bench.py. */

@@ -70,3 +70,81 @@ def test_shard_range_partitions_rows():
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+# ------------------------------------------------------------------ the library's all-gather-v (csrc/comm.cu)
+def _column(rank):
+    rng = np.random.default_rng(100 + rank)
+    lens = rng.integers(0, 9, size=rank * 5 + 4)
+    off = np.zeros(len(lens) + 1, np.uint32); off[1:] = np.cumsum(lens)
+    data = rng.integers(32, 127, size=int(off[-1]), dtype=np.uint8)
+    return off, data
+
+
+def _layout_worker(rank, world, port, q):
+    """what cpb_allgather_table does, with gloo carrying the bytes and numpy standing in for the device buffers: exchange
+    the metadata, take the row / byte bases from the library's own layout routine, place every rank's offsets and bytes at
+    its base, rebase the offsets by (byte base - first offset).  Rank 1 contributes a row-range VIEW (offsets not from 0)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from csvplus_b200 import _abi
+        from csvplus_b200.dist import allgather_layout
+        lib = _abi.load()
+        off, data = _column(rank)
+        lo = 2 if rank == 1 else 0  # a view: rows [lo, n)
+        voff = off[lo:]
+        meta = torch.tensor([len(voff) - 1, int(voff[0]), int(voff[-1])], dtype=torch.int64)
+        allmeta = [torch.zeros_like(meta) for _ in range(world)]
+        dist.all_gather(allmeta, meta)
+        m = np.stack([a.numpy() for a in allmeta]).astype(np.uint64)
+        rb, bb = allgather_layout(lib, m, 1)
+        out_off = np.zeros(int(rb[-1]) + 1, np.uint32); out_data = np.zeros(int(bb[0][-1]), np.uint8)
+        for r in range(world):  # the grouped broadcasts: root r's buffers land at its bases on every rank
+            rows, first, end = (int(x) for x in m[r])
+            seg_off = torch.from_numpy(voff[:rows].astype(np.int64)) if r == rank else torch.zeros(rows, dtype=torch.int64)
+            seg_dat = torch.from_numpy(data[first:end].copy()) if r == rank else torch.zeros(end - first, dtype=torch.uint8)
+            if rows:
+                dist.broadcast(seg_off, src=r)
+            if end > first:
+                dist.broadcast(seg_dat, src=r)
+            out_off[int(rb[r]): int(rb[r]) + rows] = (seg_off.numpy() - first + int(bb[0][r])).astype(np.uint32)
+            out_data[int(bb[0][r]): int(bb[0][r + 1])] = seg_dat.numpy()
+        out_off[-1] = int(bb[0][-1])
+        q.put((rank, out_off.tobytes(), out_data.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_library_allgather_layout_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_layout_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # expected: rows of rank 0, then rows [2, n) of rank 1
+    vals = []
+    for r in range(world):
+        off, data = _column(r)
+        lo = 2 if r == 1 else 0
+        vals += [data[off[i]:off[i + 1]].tobytes() for i in range(lo, len(off) - 1)]
+    exp_off = np.zeros(len(vals) + 1, np.uint32); exp_off[1:] = np.cumsum([len(v) for v in vals])
+    for rank, o, d in res:
+        assert o == exp_off.tobytes() and d == b"".join(vals)
+
+
+def test_allgather_layout_arithmetic():
+    from csvplus_b200 import _abi
+    from csvplus_b200.dist import allgather_layout
+    lib = _abi.load()
+    # 3 ranks, 2 columns: rows, (first, end) per column; rank 1 is empty, rank 2 is a view starting at byte 10 / 7
+    meta = np.array([[4, 0, 20, 0, 9], [0, 0, 0, 0, 0], [3, 10, 25, 7, 7]], np.uint64)
+    rb, bb = allgather_layout(lib, meta, 2)
+    assert rb.tolist() == [0, 4, 4, 7]
+    assert bb.tolist() == [[0, 20, 20, 35], [0, 9, 9, 9]]
