@@ -255,6 +255,16 @@ def bind_to_gpu_numa_node(local: int):
         return None
 
 
+def without_greatest_key(table, key_cols):
+    """the table minus every row that carries the greatest key (the last row of the sorted order): used to reach the
+    other §Q1 tail shape — the last sorted row a singleton / a member of a duplicate group"""
+    import csvplus_b200 as cp
+    ix = table.index_on(*key_cols)
+    st = ix.table()
+    last = st.rows(len(st) - 1, len(st))[0]
+    return table.filter(cp.Not(cp.Like({c: last[c] for c in key_cols})))
+
+
 def min_id_resolver(table, lo, hi):
     """the tie-order-independent resolver of SURVEY §8d cfg 5, vectorised (host user code, like the Go closure the
     reference calls once per group): for every duplicate group keep the row whose order_id is bytewise smallest"""
@@ -371,6 +381,8 @@ def main():
         assert err is None
         return t
 
+    sync0 = [0, 0]
+
     def timed(fn, steps, warmup, sampler_dev=None):
         sampler = ClockSampler(sampler_dev) if sampler_dev is not None else None  # polls through warm-up + timed steps
         for _ in range(warmup):
@@ -381,6 +393,7 @@ def main():
         torch.cuda.synchronize()
         ctx.stats(enable=True, reset=True)
         l0 = ctx.kernel_launches()
+        sync0[0] = ctx.host_syncs()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_begin = time.time()
         e0.record(stream)
@@ -388,6 +401,7 @@ def main():
         for _ in range(steps):
             r = fn(); rows = len(r); del r
         e1.record(stream)
+        sync0[1] = ctx.host_syncs() - sync0[0]
         ctx.sync(); torch.cuda.synchronize()
         t_end = time.time()
         ms = e0.elapsed_time(e1)
@@ -403,6 +417,7 @@ def main():
 
     # ---------------- device-resident timing (value)
     ms_join, out_rows, st_join, launches, clocks = timed(lambda: join_step(d_cust, d_prod, d_orders), args.steps, args.warmup, local)
+    join_syncs = sync0[1] / args.steps
     assert out_rows == ORD_ROWS, (out_rows, ORD_ROWS)  # every order matches exactly one customer and one product
     ms_parse, parse_rows, st_parse, _, _ = timed(lambda: parse_step(d_people), args.steps, args.warmup)
     peak, peak_kind = hbm_peak()
@@ -440,13 +455,13 @@ def main():
             lo, hi = ix.dup_groups()
             return len(hi) > 0 and int(hi[-1]) == len(ix)
 
-        # the second §Q1 shape: the nearest smaller row count whose last sorted row falls on the other side
+        # the second §Q1 shape: drop the rows of the greatest key until the last sorted row falls on the other side
         shape_a = tail_in_group(t_ix.index_on("cust_id", "prod_id"))
-        n_b, t_b = INDEX_ROWS, None
-        for d in range(1, 64):
-            cand = t_ix.slice(0, INDEX_ROWS - d)
+        t_b, cand = None, t_ix
+        for _ in range(40):
+            cand = without_greatest_key(cand, ("cust_id", "prod_id"))
             if tail_in_group(cand.index_on("cust_id", "prod_id")) != shape_a:
-                n_b, t_b = INDEX_ROWS - d, cand
+                t_b = cand
                 break
 
         def index_step(tab):
@@ -508,10 +523,11 @@ def main():
         h_cust, h_prod, h_orders, h_people = (ctx.host_alloc(d.nbytes) for d in (d_cust, d_prod, d_orders, d_people))
         for h, d in ((h_cust, d_cust), (h_prod, d_prod), (h_orders, d_orders), (h_people, d_people)):
             ctx.lib.cpb_memcpy_d2h(ctx.h, h.ptr, d.ptr, d.nbytes)
-        # e2e is a streaming pipeline, as a csvplus user would run a large file: the probe CSV is handed to the API in
-        # batches of complete records; two contexts (two CUDA streams) alternate batches so that the H2D copy of batch
-        # i+1 overlaps the parse+join+ToCsv of batch i and the D2H of batch i-1 (PCIe is full duplex).  The build
-        # sides go first on the main context.
+        # e2e is a streaming pipeline, as a csvplus user would run large files: one uploader thread copies products,
+        # customers and then the probe CSV in batches of complete records (pinned host -> device staging,
+        # cpb_memcpy_h2d), so the H2D engine never idles; the main context parses / indexes the build sides as they
+        # arrive; two worker contexts (two CUDA streams) parse, join and serialise the probe batches and copy the CSV
+        # text back (cpb_table_to_csv_into) — D2H runs on the other DMA engine, concurrently with the uploads.
         nbatch = max(2, args.e2e_batches)
         oview = h_orders.array()
         bounds = [0]
@@ -539,49 +555,84 @@ def main():
         ORDER_ASSUME = [("cust_id", 1), ("prod_id", 2), ("qty", 3), ("ts", 4)]
         out_bytes = [0]
 
+        # device staging the uploader fills (allocated once, like the pinned buffers): build sides + one 16-byte aligned
+        # slot per probe batch
+        up = cp.Context(local)
+        dv_cust, dv_prod = up.device_alloc(h_cust.nbytes), up.device_alloc(h_prod.nbytes)
+        dv_off = [0]
+        for b in range(nbatch):
+            dv_off.append((dv_off[-1] + (bounds[b + 1] - bounds[b]) + 255) & ~255)
+        dv_orders = up.device_alloc(dv_off[-1] + 256)
+        up.sync()
+
         def join_e2e():
             t_a = time.perf_counter()
             written = [0] * nbatch
             rows_out = [0] * nbatch
             ready = threading.Event()
+            got_prod, got_cust = threading.Event(), threading.Event()
+            got = [threading.Event() for _ in range(nbatch)]
             box = {}
             errs = []
+
+            def fail(ex):
+                errs.append(ex)
+                for ev in [ready, got_prod, got_cust] + got:
+                    ev.set()
+
+            def upload():  # one thread keeps the H2D engine busy from the first byte to the last
+                try:
+                    up.lib.cpb_memcpy_h2d(up.h, dv_prod.ptr, h_prod.ptr, h_prod.nbytes); got_prod.set()
+                    up.lib.cpb_memcpy_h2d(up.h, dv_cust.ptr, h_cust.ptr, h_cust.nbytes); got_cust.set()
+                    for b in range(nbatch):
+                        up.lib.cpb_memcpy_h2d(up.h, dv_orders.ptr + dv_off[b], h_orders.ptr + bounds[b], bounds[b + 1] - bounds[b])
+                        got[b].set()
+                except Exception as ex:
+                    fail(ex)
 
             def work(wi):
                 try:
                     w = workers[wi]
                     for b in range(wi, nbatch, 2):
-                        lo, hi = bounds[b], bounds[b + 1]
+                        got[b].wait()
+                        nb = bounds[b + 1] - bounds[b]
                         if b == 0:
-                            t, e = cp.parse_csv(w, h_orders.ptr, nbytes=hi, spec=ORDER_COLS)
+                            t, e = cp.parse_csv(w, dv_orders.ptr + dv_off[b], on_device=True, nbytes=nb, spec=ORDER_COLS)
                         else:
-                            t, e = cp.parse_csv(w, h_orders.ptr + lo, nbytes=hi - lo, spec=ORDER_ASSUME, header_from_first_row=False, num_fields=5)
+                            t, e = cp.parse_csv(w, dv_orders.ptr + dv_off[b], on_device=True, nbytes=nb, spec=ORDER_ASSUME,
+                                                header_from_first_row=False, num_fields=5)
                         assert e is None
                         ready.wait()  # the build sides are parsed / indexed concurrently on the main context
+                        if errs:
+                            return
                         j = t.join(box["cidx"], "cust_id").join(box["pidx"])
                         rows_out[b] = len(j)
                         written[b] = j.to_csv_into(h_out, out_slots[b], *SINK_COLS, header=(b == 0))
                         assert out_slots[b] + written[b] <= out_slots[b + 1]
                         del j, t
                 except Exception as ex:  # surfaced by the main thread
-                    errs.append(ex)
-                    ready.set()
-            th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+                    fail(ex)
+            th = [threading.Thread(target=upload)] + [threading.Thread(target=work, args=(i,)) for i in range(2)]
             for t in th:
                 t.start()
-            tc, err = cp.parse_csv(ctx, h_cust, spec=CUST_COLS)
-            assert err is None
-            if world > 1:
-                tc = allgather_table_nccl(ctx, tc)
-            cidx = tc.index_on("id", unique=True)
-            tp, err = cp.parse_csv(ctx, h_prod, spec=PROD_COLS)
-            assert err is None
-            pidx = tp.index_on("prod_id", unique=True)
-            warm, _ = cp.parse_csv(ctx, b"cust_id,prod_id\n0,0\n")
-            warm.join(cidx, "cust_id").join(pidx)  # builds the probe tables once, before the workers share the indices
-            ctx.sync()
-            box["cidx"], box["pidx"] = cidx, pidx
-            ready.set()
+            try:
+                got_prod.wait()
+                tp, err = cp.parse_csv(ctx, dv_prod, spec=PROD_COLS)
+                assert err is None
+                pidx = tp.index_on("prod_id", unique=True)
+                got_cust.wait()
+                tc, err = cp.parse_csv(ctx, dv_cust, spec=CUST_COLS)
+                assert err is None
+                if world > 1:
+                    tc = allgather_table_nccl(ctx, tc)
+                cidx = tc.index_on("id", unique=True)
+                warm, _ = cp.parse_csv(ctx, b"cust_id,prod_id\n0,0\n")
+                warm.join(cidx, "cust_id").join(pidx)  # builds the probe tables once, before the workers share the indices
+                ctx.sync()
+                box["cidx"], box["pidx"] = cidx, pidx
+                ready.set()
+            except Exception as ex:
+                fail(ex)
             t_b = time.perf_counter()
             for t in th:
                 t.join()
@@ -589,7 +640,7 @@ def main():
                 raise errs[0]
             out_bytes[0] = sum(written)
             if os.environ.get("BENCH_DEBUG"):
-                print("e2e step: build %.1f ms, probe+sink %.1f ms" % ((t_b - t_a) * 1e3, (time.perf_counter() - t_b) * 1e3), file=sys.stderr)
+                print("e2e step: build %.1f ms, probe+sink tail %.1f ms" % ((t_b - t_a) * 1e3, (time.perf_counter() - t_b) * 1e3), file=sys.stderr)
             return sum(rows_out)
 
         def timed_multi(fn, steps, warmup):
@@ -626,9 +677,9 @@ def main():
         e2e = {"value": world * ORD_ROWS / (ms_e2e * 1e-3), "unit": "rows/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": h_cust.nbytes + h_prod.nbytes + h_orders.nbytes, "d2h_bytes_per_step": out_bytes[0],
                "batches": nbatch, "host_numa_node": numa_node, "sink": "ToCsv(%s)" % ",".join(SINK_COLS),
-               "note": "pinned host CSV -> H2D -> parse/index/join/join/ToCsv on the GPU through the public API -> D2H of the CSV "
-                       "text of every joined row into pinned host memory; the probe file is streamed in %d batches of complete "
-                       "records over two contexts so H2D, compute and D2H overlap" % nbatch}
+               "note": "pinned host CSV -> H2D (one uploader, cpb_memcpy_h2d) -> parse/index/join/join/ToCsv on the GPU through the "
+                       "public API -> D2H of the CSV text of every joined row into pinned host memory; the probe file is streamed "
+                       "in %d batches of complete records over two contexts so H2D, compute and D2H overlap" % nbatch}
         ms_pe2e, _, _, _, _ = timed(lambda: parse_step(h_people), args.steps, args.warmup)
         parse_e2e = {"value": world * h_people.nbytes / (ms_pe2e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_pe2e,
                      "h2d_bytes_per_step": h_people.nbytes}
@@ -654,6 +705,7 @@ def main():
             "config": workload_config(world),
             "clocks": clocks, "gpu_launches": launches, "out_rows_per_gpu": out_rows,
             "kernel_ms_per_step": kernel_ms / args.steps, "host_gap_ms_per_step": ms_join - kernel_ms / args.steps,
+            "host_syncs_per_step": join_syncs,
             "e2e": e2e,
             "roofline": roof(st_join, traffic if world == 1 else None),
             "csv_parse": {"metric": "CSV parse GB/s (configs[1]: parse+SelectColumns(name,surname,id)+Filter(Like name=Amelia))",

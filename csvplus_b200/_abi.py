@@ -44,16 +44,16 @@ class KStat(C.Structure):
 SYMBOLS = [
     "cpb_abi_version", "cpb_init", "cpb_shutdown", "cpb_ctx_stream", "cpb_sync", "cpb_last_error",
     "cpb_host_alloc", "cpb_host_free", "cpb_device_alloc", "cpb_device_free", "cpb_memcpy_h2d", "cpb_memcpy_d2h",
-    "cpb_parse_csv",
+    "cpb_parse_csv", "cpb_csv_quote_parity", "cpb_parse_csv_shard", "cpb_table_col_field", "cpb_table_record_fields",
     "cpb_table_num_rows", "cpb_table_num_cols", "cpb_table_col_name", "cpb_table_find_col", "cpb_table_col_bytes",
     "cpb_table_fetch_column", "cpb_table_column_device", "cpb_table_from_host", "cpb_table_from_device",
     "cpb_table_concat", "cpb_table_select", "cpb_table_drop", "cpb_table_filter", "cpb_table_slice", "cpb_table_free",
     "cpb_index_build", "cpb_index_num_rows", "cpb_index_num_keys", "cpb_index_table", "cpb_index_find", "cpb_index_sub",
-    "cpb_index_dup_groups", "cpb_index_dedup_apply", "cpb_free", "cpb_index_free",
+    "cpb_index_dup_groups", "cpb_index_dedup_apply", "cpb_index_dedup_apply2", "cpb_free", "cpb_index_free",
     "cpb_join", "cpb_except", "cpb_table_to_csv", "cpb_table_to_csv_device", "cpb_table_to_csv_into",
     "cpb_comm_unique_id", "cpb_comm_init_rank", "cpb_init_multi", "cpb_comm_size", "cpb_comm_rank", "cpb_allgather_table",
     "cpb_allgather_tables", "cpb_allgather_u64", "cpb_allgather_layout",
-    "cpb_stats_enable", "cpb_stats_reset", "cpb_stats_get", "cpb_kernel_launches", "cpb_gen_csv",
+    "cpb_stats_enable", "cpb_stats_reset", "cpb_stats_get", "cpb_kernel_launches", "cpb_host_syncs", "cpb_gen_csv",
 ]
 
 _lib = None
@@ -83,6 +83,11 @@ def load():
         "cpb_memcpy_h2d": (i32, [vp, vp, vp, u64]),
         "cpb_memcpy_d2h": (i32, [vp, vp, vp, u64]),
         "cpb_parse_csv": (i32, [vp, vp, u64, i32, P(ReaderOpts), P(HeaderCol), i32, P(Pred), P(vp), P(Error)]),
+        "cpb_table_col_field": (i32, [vp, i32]),
+        "cpb_table_record_fields": (i32, [vp]),
+        "cpb_csv_quote_parity": (i32, [vp, vp, u64, i32, P(C.c_uint32)]),
+        "cpb_parse_csv_shard": (i32, [vp, vp, u64, i32, u64, i32, i32, C.c_uint32, P(ReaderOpts), P(HeaderCol), i32, P(Pred), P(vp),
+                                      P(u64), P(Error)]),
         "cpb_table_num_rows": (i64, [vp]),
         "cpb_table_num_cols": (i32, [vp]),
         "cpb_table_col_name": (i32, [vp, i32, P(Str)]),
@@ -106,6 +111,7 @@ def load():
         "cpb_index_sub": (i32, [vp, vp, P(Str), i32, P(vp)]),
         "cpb_index_dup_groups": (i32, [vp, vp, P(i64), P(P(i64)), P(P(i64))]),
         "cpb_index_dedup_apply": (i32, [vp, vp, i64, P(i64), i32]),
+        "cpb_index_dedup_apply2": (i32, [vp, vp, i64, P(i64), vp, i32, P(Error)]),
         "cpb_free": (None, [vp]),
         "cpb_index_free": (None, [vp]),
         "cpb_join": (i32, [vp, vp, vp, P(Str), i32, P(vp), P(Error)]),
@@ -126,6 +132,7 @@ def load():
         "cpb_stats_reset": (i32, [vp]),
         "cpb_stats_get": (i32, [vp, P(KStat), i32, P(i32)]),
         "cpb_kernel_launches": (u64, [vp]),
+        "cpb_host_syncs": (u64, [vp]),
         "cpb_gen_csv": (i32, [vp, i32, u64, u64, u64, u64, u64, i32, i32, vp, u64, P(u64)]),
     }
     for name, (res, args) in sig.items():

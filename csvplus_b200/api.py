@@ -120,6 +120,9 @@ class Context:
     def kernel_launches(self) -> int:
         return self.lib.cpb_kernel_launches(self.h)
 
+    def host_syncs(self) -> int:
+        return self.lib.cpb_host_syncs(self.h)
+
     # ---- staging memory
     def host_alloc(self, n: int) -> "HostBuffer":
         return HostBuffer(self, n)
@@ -312,6 +315,12 @@ class Table:
         n = (len(self) if hi is None else hi) - lo
         return [{c: _dec(vals[c][i]) for c in cols} for i in range(n)]
 
+    def parsed_from(self) -> tuple:
+        """(name -> field index of every column, field count of the file's first record) of a parsed table: the resolved
+        header that the shards of a file after the first are given (cpb_table_col_field / cpb_table_record_fields)"""
+        cols = self.columns
+        return ({c: self.ctx.lib.cpb_table_col_field(self.h, i) for i, c in enumerate(cols)}, self.ctx.lib.cpb_table_record_fields(self.h))
+
     def device_column(self, name: str):
         """raw device pointers (offsets uint32[n+1], data) for zero-copy interop (torch / NCCL)"""
         po, pd = C.c_void_p(), C.c_void_p()
@@ -472,6 +481,56 @@ def parse_csv(ctx: Context, data, *, on_device=False, nbytes=None, delimiter=","
     return Table(ctx, h), None
 
 
+def _input_ptr(data, nbytes, on_device, keep):
+    if isinstance(data, DeviceBuffer):
+        return data.ptr, data.nbytes if nbytes is None else nbytes, True
+    if isinstance(data, HostBuffer):
+        return data.ptr, data.nbytes if nbytes is None else nbytes, on_device
+    if isinstance(data, np.ndarray):
+        a = np.ascontiguousarray(data, np.uint8); keep.append(a)
+        return a.ctypes.data, a.size if nbytes is None else nbytes, on_device
+    if isinstance(data, int):
+        return data, nbytes, on_device
+    b = bytes(data); keep.append(b)
+    return C.cast(C.c_char_p(b), C.c_void_p).value, len(b) if nbytes is None else nbytes, on_device
+
+
+def csv_quote_parity(ctx: Context, data, *, nbytes=None, on_device=False) -> int:
+    """cpb_csv_quote_parity: parity of the quote bytes of a shard's own byte range"""
+    keep = []
+    ptr, n, dev = _input_ptr(data, nbytes, on_device, keep)
+    out = C.c_uint32()
+    st = ctx.lib.cpb_csv_quote_parity(ctx.h, C.c_void_p(ptr), n, int(dev), C.byref(out))
+    if st:
+        _raise(st, None, ctx)
+    return out.value
+
+
+def parse_csv_shard(ctx: Context, data, *, own_bytes: int, shard_index: int, is_last: bool, initial_parity: int, nbytes=None, on_device=False,
+                    delimiter=",", num_fields=0, header_from_first_row=True, spec: list | None = None, pred: Predicate | None = None):
+    """cpb_parse_csv_shard.  Returns (Table, records owned by the shard, DataSourceError | None) — the error's Line is the
+    LOCAL 0-based ordinal of the failing record among the shard's records."""
+    opts = _abi.ReaderOpts(ord(delimiter), 0, num_fields, 0, 0, int(header_from_first_row), 0)
+    keep = []
+    ptr, n, dev = _input_ptr(data, nbytes, on_device, keep)
+    spec = spec or []
+    sa = (_abi.HeaderCol * max(1, len(spec)))()
+    for i, (name, idx) in enumerate(spec):
+        nb = _enc(name); keep.append(nb)
+        sa[i].name.ptr, sa[i].name.len, sa[i].index = nb, len(nb), idx
+    pp = None
+    if pred is not None:
+        pc = pred._c(keep); keep.append(pc); pp = C.byref(pc)
+    h = C.c_void_p(); e = _abi.Error(); recs = C.c_uint64()
+    st = ctx.lib.cpb_parse_csv_shard(ctx.h, C.c_void_p(ptr), n, int(dev), own_bytes, shard_index, int(is_last), initial_parity, C.byref(opts), sa,
+                                     len(spec), pp, C.byref(h), C.byref(recs), C.byref(e))
+    if st == 1 and h.value:
+        return Table(ctx, h), recs.value, DataSourceError(e.line, e.msg.decode("utf-8", "replace"), e.kind)
+    if st:
+        _raise(st, e, ctx)
+    return Table(ctx, h), recs.value, None
+
+
 # ------------------------------------------------------------------ Index (csvplus.go:610-705)
 class Index:
     def __init__(self, ctx: Context, h, columns: list[str]):
@@ -533,34 +592,34 @@ class Index:
             _raise(st, None, self.ctx)
 
     def ResolveDuplicates(self, resolve: Callable[[list[Row]], Row | None], bug_compatible: bool = True):
-        """csvplus.go:651-653 / dedup :810-867.  `resolve` gets each group of rows with equal keys and returns one
-        of them (kept), an empty row / None (group dropped), or raises.  The returned row must be one of the
-        group's rows (the ABI keeps rows by position)."""
-        ng = C.c_int64(); lo = C.POINTER(C.c_int64)(); hi = C.POINTER(C.c_int64)()
-        st = self.ctx.lib.cpb_index_dup_groups(self.ctx.h, self.h, C.byref(ng), C.byref(lo), C.byref(hi))
-        if st:
-            _raise(st, None, self.ctx)
-        n = ng.value
-        keep = (C.c_int64 * max(1, n))()
+        """csvplus.go:651-653 / dedup :810-867.  `resolve` gets each group of rows with equal keys and returns the row to
+        keep — one of the group's rows or any other row with the index's columns (:846 stores whatever comes back,
+        without re-sorting) — or an empty row / None to drop the group, or raises (the index is left unchanged)."""
+        lo, hi = self.dup_groups()
+        n = len(lo)
+        keep = np.full(max(1, n), -1, np.int64)
+        replacements: list[Row] = []
         t = self.table()
-        try:
-            for g in range(n):
-                rows = t.rows(lo[g], hi[g])
-                chosen = resolve(rows)
-                if not chosen or len(chosen) < len(self.columns):  # csvplus.go:845
-                    keep[g] = -1
-                    continue
-                pick = next((i for i, r in enumerate(rows) if r is chosen), None)
-                if pick is None:
-                    pick = next((i for i, r in enumerate(rows) if r == chosen), None)
-                if pick is None:
-                    raise CsvPlusError("ResolveDuplicates: the resolver must return one of the rows it was given")
+        for g in range(n):
+            rows = t.rows(int(lo[g]), int(hi[g]))
+            chosen = resolve(rows)
+            if not chosen or len(chosen) < len(self.columns):  # csvplus.go:845
+                keep[g] = -1
+                continue
+            pick = next((i for i, r in enumerate(rows) if r is chosen), None)
+            if pick is None:
+                pick = next((i for i, r in enumerate(rows) if r == chosen), None)
+            if pick is None:
+                keep[g] = -2 - len(replacements)
+                replacements.append(chosen)
+            else:
                 keep[g] = lo[g] + pick
-        finally:
-            self.ctx.lib.cpb_free(lo); self.ctx.lib.cpb_free(hi)
-        st = self.ctx.lib.cpb_index_dedup_apply(self.ctx.h, self.h, n, keep, int(bug_compatible))
+        rt = Table.from_rows(self.ctx, replacements, columns=t.columns) if replacements else None
+        e = _abi.Error()
+        st = self.ctx.lib.cpb_index_dedup_apply2(self.ctx.h, self.h, n, keep.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 rt.h if rt is not None else None, int(bug_compatible), C.byref(e))
         if st:
-            _raise(st, None, self.ctx)
+            _raise(st, e, self.ctx)
 
 
 # ------------------------------------------------------------------ Reader (csvplus.go:922-1146)

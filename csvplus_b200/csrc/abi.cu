@@ -187,7 +187,7 @@ const char* cpb_last_error(cpb_ctx* h) { return h ? h->c.last_error.c_str() : ""
 int cpb_sync(cpb_ctx* h) {
     Ctx* c = &h->c; DeviceGuard g(c);
     CPB_TRY(c, nullptr)
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     return CPB_OK;
     CPB_CATCH(c, nullptr)
 }
@@ -202,7 +202,7 @@ int cpb_host_alloc(cpb_ctx* h, uint64_t n, void** out) {
 int cpb_host_free(cpb_ctx* h, void* p) {
     Ctx* c = &h->c; DeviceGuard g(c);
     CPB_TRY(c, nullptr)
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     CPB_CUDA(cudaFreeHost(p));
     return CPB_OK;
     CPB_CATCH(c, nullptr)
@@ -227,7 +227,7 @@ int cpb_memcpy_h2d(cpb_ctx* h, void* dst, const void* src, uint64_t n) {
     Ctx* c = &h->c; DeviceGuard g(c);
     CPB_TRY(c, nullptr)
     CPB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     return CPB_OK;
     CPB_CATCH(c, nullptr)
 }
@@ -235,7 +235,7 @@ int cpb_memcpy_d2h(cpb_ctx* h, void* dst, const void* src, uint64_t n) {
     Ctx* c = &h->c; DeviceGuard g(c);
     CPB_TRY(c, nullptr)
     CPB_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     return CPB_OK;
     CPB_CATCH(c, nullptr)
 }
@@ -272,6 +272,57 @@ int cpb_parse_csv(cpb_ctx* h, const void* bytes, uint64_t nbytes, int on_device,
     CPB_CATCH(c, err)
 }
 
+// ------------------------------------------------------------------ byte-range shards of one file
+static const uint8_t* stage_input(Ctx* c, const void* bytes, uint64_t nbytes, int on_device, Buf& staged) {
+    if (on_device) return (const uint8_t*)bytes;
+    staged = dev_alloc(c, (nbytes + (32u << 20)) / (32u << 20) * (32u << 20));
+    CPB_CUDA(cudaMemsetAsync(staged->as<uint8_t>() + (nbytes & ~15ull), 0, 32, c->stream));
+    if (nbytes) {
+        KernelTimer kt(c, "h2d_input", nbytes, 0);
+        CPB_CUDA(cudaMemcpyAsync(staged->p, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    return staged->as<uint8_t>();
+}
+int cpb_csv_quote_parity(cpb_ctx* h, const void* bytes, uint64_t nbytes, int on_device, uint32_t* parity) {
+    if (!h || !parity || (nbytes && !bytes)) return CPB_ERR_ARG;
+    Ctx* c = &h->c; DeviceGuard g(c);
+    CPB_TRY(c, nullptr)
+    Buf staged;
+    const uint8_t* dev = stage_input(c, bytes, nbytes, on_device, staged);
+    if ((reinterpret_cast<uintptr_t>(dev) & 15) != 0) throw ArgError{CPB_ERR_ARG, "device input must be 16-byte aligned"};
+    *parity = quote_parity(c, dev, nbytes);
+    return CPB_OK;
+    CPB_CATCH(c, nullptr)
+}
+int cpb_parse_csv_shard(cpb_ctx* h, const void* bytes, uint64_t nbytes, int on_device, uint64_t own_bytes, int shard_index, int is_last,
+                        uint32_t initial_parity, const cpb_reader_opts* opts, const cpb_header_col* spec, int nspec, const cpb_pred* filter,
+                        cpb_table** out, uint64_t* records, cpb_error* err) {
+    if (!h || !out || !opts || (nbytes && !bytes) || nspec < 0 || shard_index < 0) return CPB_ERR_ARG;
+    Ctx* c = &h->c; DeviceGuard g(c);
+    clear_error(err);
+    *out = nullptr;
+    CPB_TRY(c, err)
+    std::vector<std::pair<std::string, int>> sp;
+    for (int i = 0; i < nspec; i++) sp.emplace_back(to_string(spec[i].name), spec[i].index);
+    Buf staged;
+    const uint8_t* dev = stage_input(c, bytes, nbytes, on_device, staged);
+    uint64_t recs = 0;
+    ShardArgs sh{own_bytes, shard_index, is_last != 0, initial_parity, &recs};
+    bool had_error = false; DataError de{};
+    auto t = parse_csv(c, dev, nbytes, *opts, sp, filter, &had_error, &de, &sh);
+    if (records) *records = recs;
+    *out = wrap(t);
+    if (had_error) {
+        // the line is LOCAL: (0-based) ordinal of the failing record among this shard's records; the host adds the records
+        // of the shards before it and the reader's base (csvplus.go:1102-1137)
+        const uint64_t base = opts->header_from_first_row ? 2 : 1;
+        fill_error(err, de.kind, de.column_index, de.line >= base ? de.line - base : 0, de.has_line, de.msg);
+        return CPB_ERR_DATA;
+    }
+    return CPB_OK;
+    CPB_CATCH(c, err)
+}
+
 // ------------------------------------------------------------------ tables
 int64_t cpb_table_num_rows(const cpb_table* t) { return t ? t->t->nrows : -1; }
 int cpb_table_num_cols(const cpb_table* t) { return t ? (int)t->t->cols.size() : -1; }
@@ -281,6 +332,11 @@ int cpb_table_col_name(const cpb_table* t, int col, cpb_str* out) {
     return CPB_OK;
 }
 int cpb_table_find_col(const cpb_table* t, cpb_str name) { return t ? t->t->find(to_string(name)) : -1; }
+int cpb_table_col_field(const cpb_table* t, int col) {
+    if (!t || col < 0 || col >= (int)t->t->src_field.size()) return -1;
+    return t->t->src_field[col];
+}
+int cpb_table_record_fields(const cpb_table* t) { return t ? t->t->record_fields : -1; }
 
 int cpb_table_col_bytes(cpb_ctx* h, const cpb_table* t, int col, int64_t lo, int64_t hi, uint64_t* nbytes) {
     Ctx* c = &h->c; DeviceGuard g(c);
@@ -290,7 +346,7 @@ int cpb_table_col_bytes(cpb_ctx* h, const cpb_table* t, int col, int64_t lo, int
     uint32_t e[2];
     CPB_CUDA(cudaMemcpyAsync(&e[0], T.cols[col].off() + lo, 4, cudaMemcpyDeviceToHost, c->stream));
     CPB_CUDA(cudaMemcpyAsync(&e[1], T.cols[col].off() + hi, 4, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     *nbytes = e[1] - e[0];
     return CPB_OK;
     CPB_CATCH(c, nullptr)
@@ -305,14 +361,14 @@ int cpb_table_fetch_column(cpb_ctx* h, const cpb_table* t, int col, int64_t lo, 
     size_t cnt = (size_t)(hi - lo) + 1;
     std::vector<uint32_t> tmp(cnt);
     CPB_CUDA(cudaMemcpyAsync(tmp.data(), T.cols[col].off() + lo, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     uint64_t total = tmp[cnt - 1] - tmp[0];
     if (offsets_out) for (size_t i = 0; i < cnt; i++) offsets_out[i] = (int64_t)(tmp[i] - tmp[0]);
     if (data_out) {
         if (total > cap) throw ArgError{CPB_ERR_ARG, "data_out too small"};
         if (total) {
             CPB_CUDA(cudaMemcpyAsync(data_out, T.cols[col].bytes() + tmp[0], total, cudaMemcpyDeviceToHost, c->stream));
-            CPB_CUDA(cudaStreamSynchronize(c->stream));
+            sync_stream(c);
         }
     }
     return CPB_OK;
@@ -343,7 +399,7 @@ int cpb_table_from_host(cpb_ctx* h, int ncols, const cpb_str* names, const int64
         uint64_t total = off.back();
         col.data = dev_alloc(c, total + 16);
         if (total) CPB_CUDA(cudaMemcpyAsync(col.data->p, data[i] + offsets[i][0], total, cudaMemcpyHostToDevice, c->stream));
-        CPB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_stream(c);
         t->cols.push_back(col);
     }
     *out = wrap(t);
@@ -456,26 +512,28 @@ int cpb_index_build(cpb_ctx* h, const cpb_table* t, const cpb_str* key_cols, int
         for (int j = i + 1; j < nkeys; j++)
             if (keys[i] == keys[j]) throw ArgError{CPB_ERR_ARG, "duplicate column name(s) in CreateIndex()"};  // :714-716
     DataError de{}; bool failed = false;
-    auto ix = build_index(c, *t->t, keys, unique != 0, &de, &failed);
+    auto ix = build_index(c, t->t, keys, unique != 0, &de, &failed);
     if (failed) { fill_error(err, de.kind, de.column_index, de.line, de.has_line, de.msg); return CPB_ERR_DATA; }
     *out = new cpb_index{ix};
     return CPB_OK;
     CPB_CATCH(c, err)
 }
-int64_t cpb_index_num_rows(const cpb_index* ix) { return ix ? ix->ix->table->nrows : -1; }
+int64_t cpb_index_num_rows(const cpb_index* ix) { return ix ? ix->ix->nrows : -1; }
 int cpb_index_num_keys(const cpb_index* ix) { return ix ? (int)ix->ix->key_cols.size() : -1; }
 int cpb_index_table(cpb_ctx* h, const cpb_index* ix, cpb_table** out) {
-    (void)h;
-    *out = wrap(ix->ix->table);
+    Ctx* c = &h->c; DeviceGuard g(c);
+    CPB_TRY(c, nullptr)
+    *out = wrap(sorted_table(c, *ix->ix));
     return CPB_OK;
+    CPB_CATCH(c, nullptr)
 }
 int cpb_index_find(cpb_ctx* h, const cpb_index* ix, const cpb_str* values, int n, cpb_table** out) {
     Ctx* c = &h->c; DeviceGuard g(c);
     CPB_TRY(c, nullptr)
     if (n > (int)ix->ix->key_cols.size()) throw ArgError{CPB_ERR_ARG, "too many columns in indexImpl.find()"};  // csvplus.go:876-878
-    int64_t lo = 0, hi = ix->ix->table->nrows;
+    int64_t lo = 0, hi = ix->ix->nrows;
     if (n > 0) find_range(c, *ix->ix, str_list(values, n), &lo, &hi);
-    const Table& T = *ix->ix->table;
+    const Table& T = *sorted_table(c, *ix->ix);
     auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = hi - lo;
     for (auto col : T.cols) { col.row0 += lo; r->cols.push_back(col); }
     *out = wrap(r);
@@ -486,14 +544,14 @@ int cpb_index_sub(cpb_ctx* h, const cpb_index* ix, const cpb_str* values, int n,
     Ctx* c = &h->c; DeviceGuard g(c);
     CPB_TRY(c, nullptr)
     if (n >= (int)ix->ix->key_cols.size()) throw ArgError{CPB_ERR_ARG, "too many values in SubIndex()"};  // csvplus.go:633-635
-    int64_t lo = 0, hi = ix->ix->table->nrows;
+    int64_t lo = 0, hi = ix->ix->nrows;
     if (n > 0) find_range(c, *ix->ix, str_list(values, n), &lo, &hi);
     // rows are already sorted on the remaining key columns inside the range: rebuild the index image on the slice
     auto view = std::make_shared<Table>(); view->ctx = c; view->nrows = hi - lo;
-    for (auto col : ix->ix->table->cols) { col.row0 += lo; view->cols.push_back(col); }
+    for (auto col : sorted_table(c, *ix->ix)->cols) { col.row0 += lo; view->cols.push_back(col); }
     std::vector<std::string> keys(ix->ix->key_cols.begin() + n, ix->ix->key_cols.end());
     DataError de{}; bool failed = false;
-    auto sub = build_index(c, *view, keys, false, &de, &failed);
+    auto sub = build_index(c, view, keys, false, &de, &failed);
     if (failed) throw de;
     *out = new cpb_index{sub};
     return CPB_OK;
@@ -518,6 +576,16 @@ int cpb_index_dedup_apply(cpb_ctx* h, cpb_index* ix, int64_t ngroups, const int6
     index_dedup_apply(c, *ix->ix, k, bug_compatible != 0);
     return CPB_OK;
     CPB_CATCH(c, nullptr)
+}
+int cpb_index_dedup_apply2(cpb_ctx* h, cpb_index* ix, int64_t ngroups, const int64_t* keep, const cpb_table* replacements,
+                           int bug_compatible, cpb_error* err) {
+    Ctx* c = &h->c; DeviceGuard g(c);
+    clear_error(err);
+    CPB_TRY(c, err)
+    std::vector<int64_t> k(keep, keep + (ngroups > 0 ? ngroups : 0));
+    index_dedup_apply(c, *ix->ix, k, bug_compatible != 0, replacements ? replacements->t.get() : nullptr);
+    return CPB_OK;
+    CPB_CATCH(c, err)
 }
 void cpb_index_free(cpb_index* ix) {
     if (!ix) return;
@@ -571,7 +639,7 @@ static int to_csv_common(cpb_ctx* h, const cpb_table* t, const cpb_str* cols, in
         void* hp = nullptr;
         CPB_CUDA(cudaMallocHost(&hp, total ? total : 1));
         if (total) CPB_CUDA(cudaMemcpyAsync(hp, out->p, total, cudaMemcpyDeviceToHost, c->stream));
-        CPB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_stream(c);
         *bytes = hp;
     } else {
         void* dp = nullptr;
@@ -608,7 +676,7 @@ int cpb_table_to_csv_into(cpb_ctx* h, const cpb_table* t, const cpb_str* cols, i
         KernelTimer kt(c, "d2h_output", *nbytes, 0);
         CPB_CUDA(cudaMemcpyAsync(host_dst, out->as<uint8_t>() + skip, *nbytes, cudaMemcpyDeviceToHost, c->stream));
     }
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     return CPB_OK;
     CPB_CATCH(c, err)
 }
@@ -642,5 +710,6 @@ int cpb_stats_get(cpb_ctx* h, cpb_kstat* out, int cap, int* n) {
     return CPB_OK;
 }
 uint64_t cpb_kernel_launches(cpb_ctx* h) { return h ? h->c.launches : 0; }
+uint64_t cpb_host_syncs(cpb_ctx* h) { return h ? h->c.host_syncs : 0; }
 
 }  // extern "C"

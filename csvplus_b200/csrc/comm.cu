@@ -150,7 +150,7 @@ void job_sizes(GatherJob& j) {  // the one host round trip
     j.meta.resize((size_t)M * c->nranks);
     uint64_t* h = (uint64_t*)c->pinned_scratch(j.meta.size() * 8);
     CPB_CUDA(cudaMemcpyAsync(h, j.meta_all->p, j.meta.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     memcpy(j.meta.data(), h, j.meta.size() * 8);
 }
 void job_data_collective(GatherJob& j) {  // inside ncclGroupStart/End
@@ -317,7 +317,7 @@ int cpb_allgather_u64(cpb_ctx* h, const uint64_t* in, int count, uint64_t* out) 
     CPB_CUDA(cudaMemcpyAsync(a->p, hp, (size_t)count * 8, cudaMemcpyHostToDevice, c->stream));
     CPB_NCCL(nccl().AllGather(a->p, b->p, (size_t)count, ncclUint64, (ncclComm_t)c->comm, c->stream));
     CPB_CUDA(cudaMemcpyAsync(hp + count, b->p, (size_t)count * 8 * c->nranks, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     memcpy(out, hp + count, (size_t)count * 8 * c->nranks);
     return CPB_OK;
     CPB_CATCH(c, nullptr)

@@ -76,6 +76,10 @@ struct Table {
     int64_t nrows = 0;
     uint64_t first_line = 0;  // DataSourceError.Line the source reports for row 0 (csvplus.go:1137 / :243)
     std::vector<Column> cols;
+    // set by the parser: the field index every column was read from and the field count of the file's first record —
+    // what the shards of a file after the first need instead of the header row (cpb_parse_csv_shard)
+    std::vector<int> src_field;
+    int record_fields = 0;
     int find(const std::string& name) const {
         for (size_t i = 0; i < cols.size(); i++) if (cols[i].name == name) return (int)i;
         return -1;
@@ -108,7 +112,24 @@ struct RowSlots {
 };
 struct Index {
     Ctx* ctx = nullptr;
-    std::shared_ptr<Table> table;      // sorted rows
+    // The sorted rows exist in two forms.  A join needs neither the sorted columns nor their offsets: it probes the
+    // hash table (built from the sorted key image) and fetches payload through row slots laid out straight from the
+    // source rows + the sort permutation.  So the index build keeps (src, perm) and the physically sorted table is
+    // materialised only when something iterates / looks up / dedups the index (sorted_table()).
+    std::shared_ptr<Table> src;        // the rows as they were given to IndexOn (unsorted); null after a dedup
+    Buf perm;                          // uint32[nrows]: sorted position -> row of src
+    int64_t nrows = 0;
+    std::shared_ptr<Table> table;      // sorted rows (lazily materialised, under `mu`)
+    // A UNIQUE index whose duplicate check passed is not even sorted until something needs the order (iteration, Find,
+    // SubIndex, a prefix join, dedup): a full-key join only needs "key -> row", which the hash table built over the rows
+    // in SOURCE order gives (and that build doubles as the duplicate check: every key must find itself).  `uimage` is the
+    // key image in source order; `sorted` tells whether perm / image (sorted order) exist yet (ensure_sorted()).
+    Buf uimage;
+    bool sorted = true;
+    std::map<int, HashTable> hash_src;                   // probe tables over the source order (payload = source row)
+    std::map<std::vector<int>, RowSlots> row_slots_src;  // row slots in source order (filled sequentially, no permutation)
+    const Table& schema() const { return table ? *table : *src; }  // column names / count only
+    bool unique = false;               // built by UniqueIndexOn and verified: every full key occurs once
     std::vector<std::string> key_cols; // index.impl.columns
     std::vector<int> key_col_idx;      // positions in table->cols
     std::vector<uint32_t> key_width;   // per key column: max value length (bytes) in this index
@@ -141,6 +162,7 @@ struct Ctx {
     void* pinned = nullptr; size_t pinned_n = 0;
     // multi-GPU (comm.cu): ncclComm_t of this rank, null for a single-GPU ctx
     void* comm = nullptr; int nranks = 1, rank = 0; bool comm_owned = false;
+    Ctx* alloc_for = nullptr;  // see dev_alloc
     // host synchronisations this ctx has issued (cudaStreamSynchronize on its stream): a pipeline step should need few
     uint64_t host_syncs = 0;
 
@@ -155,13 +177,24 @@ struct KernelTimer {
     ~KernelTimer();
 };
 
+// every blocking wait of the host on a ctx stream goes through here and is counted (cpb_host_syncs): a pipeline step
+// should need few of them
+inline void sync_stream(Ctx* c) {
+    c->host_syncs++;
+    CPB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
 struct DeviceGuard {  // every entry point: select device, serialise on the ctx
     std::unique_lock<std::mutex> lk;
     explicit DeviceGuard(Ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
 };
 
-inline Buf dev_alloc(Ctx* c, size_t bytes) { return std::make_shared<DevBuf>(c, bytes ? bytes : 1); }
 inline Buf dev_alloc_owned(Ctx* owner, Ctx* user, size_t bytes) { return std::make_shared<DevBuf>(owner, user, bytes ? bytes : 1); }
+// (while a ctx builds something that stays inside an object another ctx owns, its allocations come from that owner's pool)
+inline Buf dev_alloc(Ctx* c, size_t bytes) {
+    if (c->alloc_for && c->alloc_for != c) return dev_alloc_owned(c->alloc_for, c, bytes);
+    return std::make_shared<DevBuf>(c, bytes ? bytes : 1);
+}
 
 inline std::string to_string(cpb_str s) { return std::string(s.ptr ? s.ptr : "", (size_t)s.len); }
 
@@ -172,9 +205,17 @@ int translate_exception(Ctx* c, cpb_error* err);
 
 // ------------------------------------------------------------------ cross-TU operations
 // parse.cu
+struct ShardArgs {  // byte-range shard of one file (cpb_parse_csv_shard)
+    uint64_t own_bytes;  // records starting at buffer positions (0, own_bytes] are this shard's ([0, own_bytes] for index 0)
+    int index;           // 0 = the shard holding the start of the file
+    bool is_last;        // the buffer ends where the file ends
+    uint32_t pin0;       // parity of the quote bytes of the file before this buffer
+    uint64_t* records;   // out: records owned by this shard (before filtering)
+};
 std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* dev_bytes, uint64_t n, const cpb_reader_opts& o,
                                  const std::vector<std::pair<std::string, int>>& spec, const cpb_pred* filter,
-                                 bool* had_error, DataError* derr);
+                                 bool* had_error, DataError* derr, const ShardArgs* sh = nullptr);
+uint32_t quote_parity(Ctx* c, const uint8_t* dev_bytes, uint64_t n);
 // gather.cu
 void exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, uint64_t n, uint64_t* total_dev);  // out[n] = total
 Column gather_column(Ctx* c, const Column& src, const uint32_t* row_ids, int64_t nout);
@@ -182,11 +223,14 @@ std::shared_ptr<Table> gather_rows(Ctx* c, const Table& t, const uint32_t* row_i
 std::shared_ptr<Table> filter_table(Ctx* c, const Table& t, const cpb_pred* pred);
 Column materialize(Ctx* c, const Column& col, int64_t nrows);  // view -> own compact buffers
 // rows `ids` of the index's sorted table restricted to columns `cols` (row-slot path when it pays, else gather_rows)
-std::shared_ptr<Table> gather_index_rows(Ctx* c, Index& ix, const std::vector<int>& cols, const uint32_t* ids, int64_t nout);
+std::shared_ptr<Table> gather_index_rows(Ctx* c, Index& ix, const std::vector<int>& cols, const uint32_t* ids, int64_t nout,
+                                         bool by_src = false);
 std::shared_ptr<Table> concat_tables(Ctx* c, const std::vector<const Table*>& parts);
 // sort.cu
-std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std::string>& keys, bool unique,
+std::shared_ptr<Index> build_index(Ctx* c, std::shared_ptr<Table> t, const std::vector<std::string>& keys, bool unique,
                                    DataError* derr, bool* failed);
+std::shared_ptr<Table> sorted_table(Ctx* c, Index& ix);  // materialises ix.table on first use
+void ensure_sorted(Ctx* c, Index& ix);                    // sorts a lazily-sorted unique index on first need of the order
 constexpr int MAXKEYS = 16;
 struct KeyDesc {  // key columns + the widths of the order-preserving image (sort.cu)
     int nkeys;
@@ -203,8 +247,9 @@ Buf pack_with_widths(Ctx* c, const Table& t, const std::vector<int>& kidx, const
 std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const std::vector<std::string>& cols,
                                    bool anti, DataError* derr, bool* failed);
 void find_range(Ctx* c, Index& ix, const std::vector<std::string>& values, int64_t* lo, int64_t* hi);
+bool index_has_duplicates(Ctx* c, Index& ix);  // full-key probe table over the source order + self probe
 void index_dup_groups(Ctx* c, Index& ix, std::vector<int64_t>& lo, std::vector<int64_t>& hi);
-void index_dedup_apply(Ctx* c, Index& ix, const std::vector<int64_t>& keep, bool bug_compatible);
+void index_dedup_apply(Ctx* c, Index& ix, const std::vector<int64_t>& keep, bool bug_compatible, const Table* repl = nullptr);
 // write.cu
 Buf table_to_csv(Ctx* c, const Table& t, const std::vector<int>& cols, const std::vector<std::string>& names,
                  uint64_t* nbytes, uint64_t* header_bytes);

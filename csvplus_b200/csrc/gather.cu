@@ -198,7 +198,7 @@ static std::vector<Column> gather_columns(Ctx* c, const std::vector<const Column
     }
     uint64_t* ht = (uint64_t*)c->pinned_scratch(srcs.size() * 8);
     CPB_CUDA(cudaMemcpyAsync(ht, totals->p, srcs.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     std::vector<uint64_t> tot(ht, ht + srcs.size());
     for (size_t k = 0; k < srcs.size(); k++) {
         if (tot[k] > 0xffffffffull) throw DataError{CPB_E_TOO_LARGE, (int)k, 0, false, "a result column exceeds 4 GiB; process in smaller batches"};
@@ -247,12 +247,15 @@ constexpr uint32_t RS_MAXS = 64; // bytes per slot
 struct SlotCols { int nc; const uint32_t* off[RS_MAXC]; const uint8_t* data[RS_MAXC]; };
 struct SlotOut { uint32_t* off[RS_MAXC]; uint8_t* data[RS_MAXC]; };
 
-__global__ void slot_lens_kernel(SlotCols sc, uint64_t n, uint32_t* lens, uint32_t* stat) {  // stat: [0] max row bytes, [1] a value > 255 bytes
+// (`perm`: slot r holds source row perm[r] — the slots are laid out in sorted order straight from the unsorted rows
+// of the index source; null = identity)
+__global__ void slot_lens_kernel(SlotCols sc, const uint32_t* __restrict__ perm, uint64_t n, uint32_t* lens, uint32_t* stat) {  // stat: [0] max row bytes, [1] a value > 255 bytes
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t tot = 0, packed = 0, bad = 0;
     if (r < n) {
+        const uint64_t sr = perm ? perm[r] : r;
         for (int c = 0; c < sc.nc; c++) {
-            const uint32_t l = sc.off[c][r + 1] - sc.off[c][r];
+            const uint32_t l = sc.off[c][sr + 1] - sc.off[c][sr];
             bad |= l > 255u;
             packed |= (l & 255u) << (8 * c);
             tot += l;
@@ -266,14 +269,15 @@ __global__ void slot_lens_kernel(SlotCols sc, uint64_t n, uint32_t* lens, uint32
 // one block lays out 256 consecutive slots in shared memory (row stride padded to an odd number of words: no bank
 // conflicts) and writes them with coalesced 16-byte stores
 constexpr uint32_t RS_PAD = 4;
-__global__ void __launch_bounds__(256) slot_fill_kernel(SlotCols sc, uint64_t n, uint32_t S, uint8_t* slots) {
+__global__ void __launch_bounds__(256) slot_fill_kernel(SlotCols sc, const uint32_t* __restrict__ perm, uint64_t n, uint32_t S, uint8_t* slots) {
     __shared__ __align__(16) uint8_t sm[256 * (RS_MAXS + RS_PAD)];
     const uint64_t r0 = (uint64_t)blockIdx.x * 256, r = r0 + threadIdx.x;
     uint8_t* q = sm + threadIdx.x * (S + RS_PAD);
     if (r < n) {
+        const uint64_t sr = perm ? perm[r] : r;
         uint32_t pos = 0;
         for (int c = 0; c < sc.nc; c++) {
-            const uint32_t s = sc.off[c][r], l = sc.off[c][r + 1] - s;
+            const uint32_t s = sc.off[c][sr], l = sc.off[c][sr + 1] - s;
             copy_unaligned(q + pos, sc.data[c] + s, l);
             pos += l;
         }
@@ -430,13 +434,17 @@ __global__ void __launch_bounds__(GW_WARPS * 32) slot_copy_kernel(const uint8_t*
     }
 }
 
-static RowSlots& ensure_row_slots(Ctx* c, Index& ix, const std::vector<int>& cols) {
+static RowSlots& ensure_row_slots(Ctx* c, Index& ix, const std::vector<int>& cols, bool by_src) {
     std::lock_guard<std::mutex> lk(ix.mu);
-    auto it = ix.row_slots.find(cols);
-    if (it != ix.row_slots.end()) return it->second;
+    auto& smap = by_src ? ix.row_slots_src : ix.row_slots;
+    auto it = smap.find(cols);
+    if (it != smap.end()) return it->second;
     RowSlots rs;
-    const Table& t = *ix.table;
-    const uint64_t n = (uint64_t)t.nrows;
+    // by_src: slot r = source row r (filled sequentially); else sorted order: the sorted rows if they exist, else the source
+    // rows through the permutation
+    const Table& t = by_src ? *ix.src : (ix.table ? *ix.table : *ix.src);
+    const uint32_t* perm = (by_src || ix.table) ? nullptr : ix.perm->as<uint32_t>();
+    const uint64_t n = (uint64_t)ix.nrows;
     if (n > 0 && !cols.empty() && cols.size() <= (size_t)RS_MAXC) {
         SlotCols sc{};
         sc.nc = (int)cols.size();
@@ -446,40 +454,45 @@ static RowSlots& ensure_row_slots(Ctx* c, Index& ix, const std::vector<int>& col
         uint64_t col_bytes = n * 4 * sc.nc;
         {
             KernelTimer kt(c, "slot_build", col_bytes + n * 4);
-            slot_lens_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sc, n, lens->as<uint32_t>(), stat->as<uint32_t>());
+            slot_lens_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sc, perm, n, lens->as<uint32_t>(), stat->as<uint32_t>());
             CPB_CUDA(cudaGetLastError());
         }
         uint32_t* hs = (uint32_t*)c->pinned_scratch(8);
         CPB_CUDA(cudaMemcpyAsync(hs, stat->p, 8, cudaMemcpyDeviceToHost, c->stream));
-        CPB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_stream(c);
         if (hs[1] == 0 && hs[0] <= RS_MAXS) {
             rs.S = std::max<uint32_t>(16, (hs[0] + 15) & ~15u);
             rs.slots = dev_alloc_owned(ix.ctx, c, n * rs.S);
             rs.lens = lens;
             KernelTimer kt(c, "slot_build", n * rs.S * 2);
-            slot_fill_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sc, n, rs.S, rs.slots->as<uint8_t>());
+            slot_fill_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sc, perm, n, rs.S, rs.slots->as<uint8_t>());
             CPB_CUDA(cudaGetLastError());
             rs.usable = true;
         }
     }
-    CPB_CUDA(cudaStreamSynchronize(c->stream));  // complete before another context (stream) can find it in the map
-    return ix.row_slots.emplace(cols, std::move(rs)).first->second;
+    sync_stream(c);  // complete before another context (stream) can find it in the map
+    return smap.emplace(cols, std::move(rs)).first->second;
 }
 
-std::shared_ptr<Table> gather_index_rows(Ctx* c, Index& ix, const std::vector<int>& cols, const uint32_t* ids, int64_t nout) {
-    const Table& t = *ix.table;
-    Table sub; sub.ctx = c; sub.nrows = t.nrows; sub.first_line = t.first_line;
-    for (int ci : cols) sub.cols.push_back(t.cols[ci]);
+std::shared_ptr<Table> gather_index_rows(Ctx* c, Index& ix, const std::vector<int>& cols, const uint32_t* ids, int64_t nout, bool by_src) {
+    auto plain = [&]() {  // per-column gather: from the source rows (ids = source rows), or from the physically sorted rows
+        std::shared_ptr<Table> keep = by_src ? ix.src : sorted_table(c, ix);
+        const Table& st = *keep;
+        Table sub; sub.ctx = c; sub.nrows = st.nrows; sub.first_line = st.first_line;
+        for (int ci : cols) sub.cols.push_back(st.cols[ci]);
+        return gather_rows(c, sub, ids, nout);
+    };
     static const bool disabled = getenv("CPB_NO_ROWSLOTS") != nullptr;
     bool use = !disabled && ids != nullptr && nout > 0 && !cols.empty() && cols.size() <= (size_t)RS_MAXC;
     if (use) {
         bool built;
-        { std::lock_guard<std::mutex> lk(ix.mu); built = ix.row_slots.count(cols) != 0; }
-        if (!built && nout < t.nrows) use = false;  // laying the slots out costs about one gather of the whole index
+        { std::lock_guard<std::mutex> lk(ix.mu); built = (by_src ? ix.row_slots_src : ix.row_slots).count(cols) != 0; }
+        if (!built && nout < ix.nrows) use = false;  // laying the slots out costs about one gather of the whole index
     }
-    if (!use) return gather_rows(c, sub, ids, nout);
-    RowSlots& rs = ensure_row_slots(c, ix, cols);
-    if (!rs.usable) return gather_rows(c, sub, ids, nout);
+    if (!use) return plain();
+    RowSlots& rs = ensure_row_slots(c, ix, cols, by_src);
+    if (!rs.usable) return plain();
+    const Table& t = ix.schema();
 
     const int nc = (int)cols.size();
     auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = nout; r->first_line = t.first_line;
@@ -506,7 +519,7 @@ std::shared_ptr<Table> gather_index_rows(Ctx* c, Index& ix, const std::vector<in
     }
     uint64_t* ht = (uint64_t*)c->pinned_scratch(RS_MAXC * 8);
     CPB_CUDA(cudaMemcpyAsync(ht, totals, nc * 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     uint64_t all = 0;
     for (int k = 0; k < nc; k++) {
         if (ht[k] > 0xffffffffull) throw DataError{CPB_E_TOO_LARGE, k, 0, false, "a result column exceeds 4 GiB; process in smaller batches"};
@@ -569,7 +582,7 @@ std::shared_ptr<Table> filter_table(Ctx* c, const Table& t, const cpb_pred* pred
     exclusive_scan_u32(c, flags->as<uint32_t>(), pos->as<uint32_t>(), n, total->as<uint64_t>());
     uint64_t* ht = (uint64_t*)c->pinned_scratch(8);
     CPB_CUDA(cudaMemcpyAsync(ht, total->p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     const uint64_t m = *ht;
     Buf ids = dev_alloc(c, (m + 1) * 4);
     {
@@ -604,7 +617,7 @@ std::shared_ptr<Table> concat_tables(Ctx* c, const std::vector<const Table*>& pa
             CPB_CUDA(cudaMemcpyAsync(hp + 2 * (p * K + k), off, 4, cudaMemcpyDeviceToHost, c->stream));
             CPB_CUDA(cudaMemcpyAsync(hp + 2 * (p * K + k) + 1, off + parts[p]->nrows, 4, cudaMemcpyDeviceToHost, c->stream));
         }
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     memcpy(ext.data(), hp, ext.size() * 4);
     auto r = std::make_shared<Table>(); r->ctx = c; r->nrows = nrows; r->first_line = first.first_line;
     for (size_t k = 0; k < K; k++) {

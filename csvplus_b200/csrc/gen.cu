@@ -129,7 +129,7 @@ extern "C" int cpb_gen_csv(cpb_ctx* h, int kind, uint64_t seed, uint64_t row_lo,
     exclusive_scan_u32(c, len->as<uint32_t>(), len->as<uint32_t>(), rows, total->as<uint64_t>());
     uint64_t* ht = (uint64_t*)c->pinned_scratch(8);
     CPB_CUDA(cudaMemcpyAsync(ht, total->p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     if (*ht > 0xffffffffull) throw ArgError{CPB_ERR_ARG, "generate at most 4 GiB per call (split the row range)"};
     *nbytes = *ht + gp.header_len;
     if (dst) {
@@ -139,7 +139,7 @@ extern "C" int cpb_gen_csv(cpb_ctx* h, int kind, uint64_t seed, uint64_t row_lo,
             gen_write_kernel<<<(uint32_t)((rows + 255) / 256), 256, 0, c->stream>>>(gp, len->as<uint32_t>(), (uint8_t*)dst);
             CPB_CUDA(cudaGetLastError());
         }
-        CPB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_stream(c);
     }
     return CPB_OK;
     CPB_CATCH(c, nullptr)

@@ -244,28 +244,46 @@ __global__ void compact_ids2_kernel(const uint32_t* __restrict__ flags, const ui
 static uint64_t read_u64(Ctx* c, const void* dev) {
     uint64_t* h = (uint64_t*)c->pinned_scratch(8);
     CPB_CUDA(cudaMemcpyAsync(h, dev, 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     return *h;
 }
 
-static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
+__global__ void iota_heads_kernel(uint32_t* heads, uint64_t n) {  // heads[i] = i for i in [0, n]
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) heads[i] = (uint32_t)i;
+}
+
+// by_src: the table is built over the rows in SOURCE order (a lazily sorted unique index: payload = source row, key
+// image = ix.uimage); otherwise over the sorted order (payload = sorted position, key image = ix.image).
+static HashTable& ensure_hash(Ctx* c, Index& ix, int nk, bool by_src) {
     std::lock_guard<std::mutex> lk(ix.mu);
-    auto it = ix.hash.find(nk);
-    if (it != ix.hash.end()) return it->second;
+    auto& hmap = by_src ? ix.hash_src : ix.hash;
+    const Buf& image = by_src ? ix.uimage : ix.image;
+    auto it = hmap.find(nk);
+    if (it != hmap.end()) return it->second;
     HashTable ht;
     ht.nkeys = nk; ht.pbytes = prefix_bytes(ix, nk);
-    const uint64_t n = (uint64_t)ix.table->nrows;
-    Buf head = dev_alloc(c, (n + 1) * 4), pos = dev_alloc(c, (n + 1) * 4), tot = dev_alloc(c, 8);
-    {
-        KernelTimer kt(c, "hash_heads", (uint64_t)ix.image_words * n * 8 + n * 4);
-        head_flags2_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, head->as<uint32_t>());
+    const uint64_t n = (uint64_t)ix.nrows;
+    if (ix.unique && nk == (int)ix.key_cols.size()) {
+        // a verified unique index probed on its full key: every sorted row is its own run — no adjacent compare, no scan,
+        // no host round trip for the number of distinct keys
+        ht.nheads = n;
+        ht.heads = dev_alloc_owned(ix.ctx, c, (n + 1) * 4);
+        iota_heads_kernel<<<nblk(n + 1, 256), 256, 0, c->stream>>>(ht.heads->as<uint32_t>(), n);
         CPB_CUDA(cudaGetLastError());
+    } else {
+        Buf head = dev_alloc(c, (n + 1) * 4), pos = dev_alloc(c, (n + 1) * 4), tot = dev_alloc(c, 8);
+        {
+            KernelTimer kt(c, "hash_heads", (uint64_t)ix.image_words * n * 8 + n * 4);
+            head_flags2_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(image->as<uint64_t>(), n, ht.pbytes, head->as<uint32_t>());
+            CPB_CUDA(cudaGetLastError());
+        }
+        exclusive_scan_u32(c, head->as<uint32_t>(), pos->as<uint32_t>(), n, tot->as<uint64_t>());
+        ht.nheads = read_u64(c, tot->p);
+        // what stays in the index comes from the index owner's pool: the probing context may be shut down first
+        ht.heads = dev_alloc_owned(ix.ctx, c, (ht.nheads + 1) * 4);
+        compact_heads_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(head->as<uint32_t>(), pos->as<uint32_t>(), ht.heads->as<uint32_t>(), n);
     }
-    exclusive_scan_u32(c, head->as<uint32_t>(), pos->as<uint32_t>(), n, tot->as<uint64_t>());
-    ht.nheads = read_u64(c, tot->p);
-    // what stays in the index comes from the index owner's pool: the probing context may be shut down first
-    ht.heads = dev_alloc_owned(ix.ctx, c, (ht.nheads + 1) * 4);
-    compact_heads_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(head->as<uint32_t>(), pos->as<uint32_t>(), ht.heads->as<uint32_t>(), n);
     uint64_t want = std::max<uint64_t>(16, ht.nheads * 2);
     ht.nslots = 1; while (ht.nslots < want) ht.nslots <<= 1;
     // one of three probe tables: ordinal slots (+ heads + key image; shared-memory sized or wide keys), or the
@@ -275,7 +293,7 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
         ht.slots = dev_alloc_owned(ix.ctx, c, ht.nslots * 4);
         CPB_CUDA(cudaMemsetAsync(ht.slots->p, 0xff, ht.nslots * 4, c->stream));
         KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8));
-        hash_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
+        hash_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
                                                                         ht.slots->as<uint32_t>(), ht.nslots - 1);
         CPB_CUDA(cudaGetLastError());
     }
@@ -285,7 +303,7 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
         ht.slots16 = dev_alloc_owned(ix.ctx, c, ht.nslots16 * sizeof(Slot16));
         CPB_CUDA(cudaMemsetAsync(ht.slots16->p, 0, ht.nslots16 * sizeof(Slot16), c->stream));
         KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8) + ht.nslots16 * 16);
-        hash16_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
+        hash16_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
                                                                           ht.slots16->as<Slot16>(), ht.nslots16);
         CPB_CUDA(cudaGetLastError());
     } else if (ht.pbytes <= 24 && too_large_for_smem) {  // key fits a sector
@@ -293,18 +311,55 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk) {
         ht.slots32 = dev_alloc_owned(ix.ctx, c, ht.nslots32 * sizeof(Slot32));
         CPB_CUDA(cudaMemsetAsync(ht.slots32->p, 0, ht.nslots32 * sizeof(Slot32), c->stream));
         KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8) + ht.nslots32 * 32);
-        hash32_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
+        hash32_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
                                                                           ht.slots32->as<Slot32>(), ht.nslots32);
         CPB_CUDA(cudaGetLastError());
     }
-    CPB_CUDA(cudaStreamSynchronize(c->stream));  // complete before any other context (stream) can find it in the map
-    return ix.hash.emplace(nk, std::move(ht)).first->second;
+    sync_stream(c);  // complete before any other context (stream) can find it in the map
+    return hmap.emplace(nk, std::move(ht)).first->second;
+}
+
+// per probe row the matching run [lo, lo+cnt) of index rows, through whichever probe table the index has for nk columns
+static void probe_dispatch(Ctx* c, const Table& probe, const std::vector<int>& pidx, Index& ix, HashTable& ht, const Buf& iimage, int nk,
+                           uint32_t* lo, uint32_t* cnt, uint32_t* not_one) {
+    const uint64_t np = (uint64_t)probe.nrows, ni = (uint64_t)ix.nrows;
+    std::vector<uint32_t> widths(ix.key_width.begin(), ix.key_width.begin() + nk);
+    uint32_t pwords = 0;
+    Buf pimg;
+    if (!ht.slots32 && !ht.slots16) pimg = pack_with_widths(c, probe, pidx, widths, &pwords);
+    else pwords = (ht.pbytes + 7) / 8;
+    // algorithmic bytes: probe keys once + build table once
+    uint64_t algo = np * ((uint64_t)pwords * 8 + 8) + ht.nslots * 4 + ht.nheads * ((uint64_t)ht.pbytes + 4);
+    size_t smem = (ht.nslots + ht.nheads + 1) * 4;
+    KernelTimer kt(c, "join_probe", algo);
+    if (ht.slots16) {
+        KeyDesc kd{};
+        describe_keys(c, probe, pidx, widths, kd);
+        uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
+        join_probe16_kernel<<<grid, 256, 0, c->stream>>>(kd, np, ht.slots16->as<Slot16>(), ht.nslots16, lo, cnt, not_one);
+    } else if (ht.slots32) {
+        KeyDesc kd{};
+        describe_keys(c, probe, pidx, widths, kd);
+        uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
+        join_probe32_kernel<<<grid, 256, 0, c->stream>>>(kd, np, ht.slots32->as<Slot32>(), ht.nslots32, lo, cnt, not_one);
+    } else if (smem <= 200 * 1024) {
+        // (per device, and cheap: set on every launch rather than cached per process)
+        CPB_CUDA(cudaFuncSetAttribute(join_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count);
+        join_probe_kernel<true><<<grid, 256, smem, c->stream>>>(pimg->as<uint64_t>(), np, iimage->as<uint64_t>(), ni, ht.pbytes,
+                                                                ht.slots->as<uint32_t>(), ht.nslots, ht.heads->as<uint32_t>(), ht.nheads, lo, cnt, not_one);
+    } else {
+        uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
+        join_probe_kernel<false><<<grid, 256, 0, c->stream>>>(pimg->as<uint64_t>(), np, iimage->as<uint64_t>(), ni, ht.pbytes,
+                                                              ht.slots->as<uint32_t>(), ht.nslots, ht.heads->as<uint32_t>(), ht.nheads, lo, cnt, not_one);
+    }
+    CPB_CUDA(cudaGetLastError());
 }
 
 std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const std::vector<std::string>& cols, bool anti,
                                    DataError* derr, bool* failed) {
     *failed = false;
-    const uint64_t np = (uint64_t)probe.nrows, ni = (uint64_t)ix.table->nrows;
+    const uint64_t np = (uint64_t)probe.nrows, ni = (uint64_t)ix.nrows;
     const int nk = (int)cols.size();
     std::vector<int> pidx;
     for (int k = 0; k < nk; k++) {
@@ -319,8 +374,9 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
     // output schema: mergeRows(indexRow, probeRow) — probe wins name collisions (csvplus.go:571-583)
     std::vector<const Column*> icols, pcols;
     std::vector<int> icol_idx;
-    if (!anti) for (size_t q = 0; q < ix.table->cols.size(); q++)
-        if (probe.find(ix.table->cols[q].name) < 0) { icols.push_back(&ix.table->cols[q]); icol_idx.push_back((int)q); }
+    const Table& ischema = ix.schema();  // names only: the sorted columns may not be materialised
+    if (!anti) for (size_t q = 0; q < ischema.cols.size(); q++)
+        if (probe.find(ischema.cols[q].name) < 0) { icols.push_back(&ischema.cols[q]); icol_idx.push_back((int)q); }
     for (auto& col : probe.cols) pcols.push_back(&col);
 
     auto out = std::make_shared<Table>(); out->ctx = c; out->first_line = probe.first_line;
@@ -334,43 +390,15 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
     Buf lo = dev_alloc(c, np * 4), cnt = dev_alloc(c, (np + 1) * 4), flags = dev_alloc(c, 32);
     CPB_CUDA(cudaMemsetAsync(flags->p, 0, 32, c->stream));
     uint32_t* not_one = flags->as<uint32_t>() + 2;  // [0..1] = scan total
+    // a lazily sorted unique index joined on its full key: probe table and row slots over the source order
+    const bool by_src = ix.unique && ix.uimage && nk == (int)ix.key_cols.size();
+    if (ni != 0 && !by_src) ensure_sorted(c, ix);
+    const Buf& iimage = by_src ? ix.uimage : ix.image;
     if (ni == 0) {
         CPB_CUDA(cudaMemsetAsync(cnt->p, 0, (np + 1) * 4, c->stream));
     } else {
-        HashTable& ht = ensure_hash(c, ix, nk);
-        std::vector<uint32_t> widths(ix.key_width.begin(), ix.key_width.begin() + nk);
-        uint32_t pwords = 0;
-        Buf pimg;
-        if (!ht.slots32 && !ht.slots16) pimg = pack_with_widths(c, probe, pidx, widths, &pwords);
-        else pwords = (ht.pbytes + 7) / 8;
-        // algorithmic bytes: probe keys once + build table once
-        uint64_t algo = np * ((uint64_t)pwords * 8 + 8) + ht.nslots * 4 + ht.nheads * ((uint64_t)ht.pbytes + 4);
-        size_t smem = (ht.nslots + ht.nheads + 1) * 4;
-        KernelTimer kt(c, "join_probe", algo);
-        if (ht.slots16) {
-            KeyDesc kd{};
-            describe_keys(c, probe, pidx, widths, kd);
-            uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
-            join_probe16_kernel<<<grid, 256, 0, c->stream>>>(kd, np, ht.slots16->as<Slot16>(), ht.nslots16, lo->as<uint32_t>(), cnt->as<uint32_t>(), not_one);
-        } else if (ht.slots32) {
-            KeyDesc kd{};
-            describe_keys(c, probe, pidx, widths, kd);
-            uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
-            join_probe32_kernel<<<grid, 256, 0, c->stream>>>(kd, np, ht.slots32->as<Slot32>(), ht.nslots32, lo->as<uint32_t>(), cnt->as<uint32_t>(), not_one);
-        } else if (smem <= 200 * 1024) {
-            // (per device, and cheap: set on every launch rather than cached per process)
-            CPB_CUDA(cudaFuncSetAttribute(join_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count);
-            join_probe_kernel<true><<<grid, 256, smem, c->stream>>>(pimg->as<uint64_t>(), np, ix.image->as<uint64_t>(), ni, ht.pbytes,
-                                                                    ht.slots->as<uint32_t>(), ht.nslots, ht.heads->as<uint32_t>(), ht.nheads,
-                                                                    lo->as<uint32_t>(), cnt->as<uint32_t>(), not_one);
-        } else {
-            uint32_t grid = (uint32_t)std::min<uint64_t>(nblk(np, 256), (uint64_t)c->sm_count * 16);
-            join_probe_kernel<false><<<grid, 256, 0, c->stream>>>(pimg->as<uint64_t>(), np, ix.image->as<uint64_t>(), ni, ht.pbytes,
-                                                                  ht.slots->as<uint32_t>(), ht.nslots, ht.heads->as<uint32_t>(), ht.nheads,
-                                                                  lo->as<uint32_t>(), cnt->as<uint32_t>(), not_one);
-        }
-        CPB_CUDA(cudaGetLastError());
+        HashTable& ht = ensure_hash(c, ix, nk, by_src);
+        probe_dispatch(c, probe, pidx, ix, ht, iimage, nk, lo->as<uint32_t>(), cnt->as<uint32_t>(), not_one);
     }
     Buf tot = flags;
     if (anti) {
@@ -387,7 +415,7 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
     }
     uint32_t* hf = (uint32_t*)c->pinned_scratch(32);
     CPB_CUDA(cudaMemcpyAsync(hf, flags->p, 32, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     const uint64_t m = (uint64_t)hf[4] | ((uint64_t)hf[5] << 32);  // counted by the probe kernel (0 when ni == 0)
     // every probe row matched exactly one index row (the usual foreign-key join): the probe-side columns of the
     // result ARE the probe columns, in order — share their buffers instead of copying them; no scan of the counts
@@ -395,7 +423,7 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
     if (m > 0xfffffffeull) throw DataError{CPB_E_TOO_LARGE, -1, 0, false, "join result exceeds 2^32-2 rows; probe in smaller batches"};
     if (m == 0) return empty_result();
     if (probe_identity) {
-        auto gi = gather_index_rows(c, ix, icol_idx, lo->as<uint32_t>(), (int64_t)m);  // lo[i] is the single matching index row
+        auto gi = gather_index_rows(c, ix, icol_idx, lo->as<uint32_t>(), (int64_t)m, by_src);  // lo[i] is the single matching index row
         out->nrows = (int64_t)m;
         for (auto& col : gi->cols) out->cols.push_back(col);
         for (auto* p : pcols) out->cols.push_back(*p);
@@ -412,12 +440,38 @@ std::shared_ptr<Table> join_tables(Ctx* c, const Table& probe, Index& ix, const 
     }
     Table pt; pt.ctx = c; pt.nrows = (int64_t)np;
     for (auto* p : pcols) pt.cols.push_back(*p);
-    auto gi = gather_index_rows(c, ix, icol_idx, iid->as<uint32_t>(), (int64_t)m);
+    auto gi = gather_index_rows(c, ix, icol_idx, iid->as<uint32_t>(), (int64_t)m, by_src);
     auto gp = gather_rows(c, pt, pid->as<uint32_t>(), (int64_t)m);
     out->nrows = (int64_t)m;
     for (auto& col : gi->cols) out->cols.push_back(col);
     for (auto& col : gp->cols) out->cols.push_back(col);
     return out;
+}
+
+// ------------------------------------------------------------------ UniqueIndexOn without sorting
+// Every row probes the full-key table built over the rows themselves: with unique keys row r finds r.  Two rows with
+// the same key occupy two slots of one probe sequence, so at least one of them finds the other: a duplicate exists
+// iff some row does not find itself.
+__global__ void self_check_kernel(const uint32_t* __restrict__ lo, const uint32_t* __restrict__ cnt, uint64_t n, uint32_t* flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (cnt[i] != 1u || lo[i] != (uint32_t)i)) *flag = 1u;  // benign race: every writer stores 1
+}
+bool index_has_duplicates(Ctx* c, Index& ix) {
+    const uint64_t n = (uint64_t)ix.nrows;
+    const int nk = (int)ix.key_cols.size();
+    HashTable& ht = ensure_hash(c, ix, nk, true);
+    Buf lo = dev_alloc(c, n * 4), cnt = dev_alloc(c, (n + 1) * 4), flags = dev_alloc(c, 64);
+    CPB_CUDA(cudaMemsetAsync(flags->p, 0, 64, c->stream));
+    probe_dispatch(c, *ix.src, ix.key_col_idx, ix, ht, ix.uimage, nk, lo->as<uint32_t>(), cnt->as<uint32_t>(), flags->as<uint32_t>() + 2);
+    {
+        KernelTimer kt(c, "unique_check", n * 8);
+        self_check_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(lo->as<uint32_t>(), cnt->as<uint32_t>(), n, flags->as<uint32_t>() + 8);
+        CPB_CUDA(cudaGetLastError());
+    }
+    uint32_t* hf = (uint32_t*)c->pinned_scratch(64);
+    CPB_CUDA(cudaMemcpyAsync(hf, flags->p, 64, cudaMemcpyDeviceToHost, c->stream));
+    sync_stream(c);
+    return hf[8] != 0;
 }
 
 // ------------------------------------------------------------------ Index.Find: [lower, upper) of a key prefix
@@ -446,9 +500,10 @@ __global__ void find_range_kernel(const uint64_t* __restrict__ image, uint64_t n
 }
 
 void find_range(Ctx* c, Index& ix, const std::vector<std::string>& values, int64_t* lo, int64_t* hi) {
-    const uint64_t n = (uint64_t)ix.table->nrows;
+    const uint64_t n = (uint64_t)ix.nrows;
     *lo = 0; *hi = 0;
     if (n == 0) return;
+    ensure_sorted(c, ix);
     // pack the lookup values on the host with the index's widths (a handful of bytes)
     std::vector<uint8_t> img((size_t)ix.image_words * 8 + 8, 0);
     size_t b = 0;
@@ -470,7 +525,7 @@ void find_range(Ctx* c, Index& ix, const std::vector<std::string>& values, int64
     }
     uint64_t* h = (uint64_t*)c->pinned_scratch(16);
     CPB_CUDA(cudaMemcpyAsync(h, out->p, 16, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     *lo = (int64_t)h[0]; *hi = (int64_t)h[1];
 }
 

@@ -74,9 +74,40 @@ bool valid_delim(uint32_t r) {
     return r != 0 && r != '"' && r != '\r' && r != '\n' && r != 0xFFFD && r <= 0x10FFFF && !(r >= 0xD800 && r <= 0xDFFF);
 }
 
-std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cpb_reader_opts& o,
+// parity of the '"' bytes of [0, n): what a byte-range shard contributes to the quote state of the shards after it
+__global__ void quote_parity_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* out) {
+    uint32_t cnt = 0;
+    const uint64_t nv = n / 16;
+    const uint4* v = reinterpret_cast<const uint4*>(in);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 x = v[i];
+        cnt += __popc(eq_flags(x.x, 0x22222222u)) + __popc(eq_flags(x.y, 0x22222222u)) + __popc(eq_flags(x.z, 0x22222222u)) +
+               __popc(eq_flags(x.w, 0x22222222u));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) for (uint64_t i = nv * 16; i < n; i++) cnt += in[i] == '"';
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && (cnt & 1)) atomicXor(out, 1u);
+}
+uint32_t quote_parity(Ctx* c, const uint8_t* in, uint64_t n) {
+    Buf out = dev_alloc(c, 4);
+    CPB_CUDA(cudaMemsetAsync(out->p, 0, 4, c->stream));
+    if (n) {
+        KernelTimer kt(c, "quote_parity", n);
+        quote_parity_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(in, n, out->as<uint32_t>());
+        CPB_CUDA(cudaGetLastError());
+    }
+    uint32_t* h = (uint32_t*)c->pinned_scratch(4);
+    CPB_CUDA(cudaMemcpyAsync(h, out->p, 4, cudaMemcpyDeviceToHost, c->stream));
+    sync_stream(c);
+    return *h & 1u;
+}
+
+std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, const cpb_reader_opts& o_arg,
                                  const std::vector<std::pair<std::string, int>>& spec, const cpb_pred* filter,
-                                 bool* had_error, DataError* derr) {
+                                 bool* had_error, DataError* derr, const ShardArgs* sh) {
+    const uint8_t* in = in_arg;
+    uint64_t n = n_arg;
+    cpb_reader_opts o = o_arg;
     *had_error = false;
     auto fail = [&](int kind, int col, uint64_t line, const std::string& msg) {
         *had_error = true; *derr = DataError{kind, col, line, true, msg};
@@ -98,25 +129,39 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
         fail(CPB_E_INVALID_DELIM, -1, 1, "csv: invalid field or comment delimiter");
         return empty_table(spec_names);
     }
-    if (o.delimiter >= 0x80 || o.comment >= 0x80)
-        throw ArgError{CPB_ERR_UNSUPPORTED, "multi-byte Delimiter / CommentChar runes are not lowered to kernels yet"};
+    if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) throw ArgError{CPB_ERR_ARG, "device input must be 16-byte aligned"};
+    // Multi-byte Delimiter / CommentChar runes and the multi-byte Unicode spaces of TrimLeadingSpace: every occurrence
+    // is transcoded to a single byte value the input does not use (subst.cu); from here on the options are single-byte
+    Substitution sub;
+    if (needs_substitution(o)) {
+        sub = substitute_runes(c, in, n, o);
+        o.delimiter = sub.delimiter; o.comment = sub.comment;
+        if (sub.buffer) { in = sub.buffer->as<uint8_t>(); n = sub.nbytes; }
+    }
+    const SubTable* subs_dev = sub.table ? sub.table->as<SubTable>() : nullptr;
     // CommentChar / LazyQuotes / TrimLeadingSpace change what "inside quotes" means: they take the general
     // (DFA-composition, multi-pass) path of parse_general.cu; the default options take the single-pass scan.
     const bool general = o.comment != 0 || o.lazy_quotes || o.trim_leading_space;
+    if (sh) {  // a byte-range shard of one file (cpb_parse_csv_shard)
+        if (general || sub.table) throw ArgError{CPB_ERR_UNSUPPORTED, "byte-range shards take the default reader options only"};
+        if (sh->index > 0 && (o.header_from_first_row || o.num_fields == 0))
+            throw ArgError{CPB_ERR_ARG, "shards after the first need the resolved header (name -> index) and an explicit field count"};
+        if (sh->own_bytes > n) throw ArgError{CPB_ERR_ARG, "own_bytes exceeds the buffer"};
+    }
     if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) throw ArgError{CPB_ERR_ARG, "device input must be 16-byte aligned"};
 
     // ---- header kernel (first record + sampling)
     Buf hbuf = dev_alloc(c, sizeof(HeaderOut));
-    if (general) general_header(c, in, n, o, hbuf->as<HeaderOut>());
+    if (general) general_header(c, in, n, o, &sub, hbuf->as<HeaderOut>());
     else {
         KernelTimer kt(c, "csv_header", 0);
-        csv_header_kernel<<<1, 256, 0, c->stream>>>(in, n, (int)o.delimiter, hbuf->as<HeaderOut>());
+        csv_header_kernel<<<1, 256, 0, c->stream>>>(in, n, (int)o.delimiter, subs_dev, hbuf->as<HeaderOut>());
         CPB_CUDA(cudaGetLastError());
     }
     HeaderOut* h = (HeaderOut*)c->pinned_scratch(sizeof(HeaderOut));
     // only the fixed part + what is needed: copy the whole struct (≈80 KB) — small next to the input
     CPB_CUDA(cudaMemcpyAsync(h, hbuf->p, sizeof(HeaderOut), cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     if (h->truncated) throw ArgError{CPB_ERR_UNSUPPORTED, "header row larger than 16 KiB / 1024 fields"};
 
     // ---- header resolution: makeHeader, csvplus.go:1149-1206
@@ -165,7 +210,7 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
     } else {
         if (spec.empty()) throw ArgError{CPB_ERR_ARG, "Empty header spec"};  // csvplus.go:999-1001
         for (auto& s : spec) { if (s.second < 0) throw ArgError{CPB_ERR_ARG, "header spec: negative index for column " + s.first}; cols.push_back(s); }
-        data_start = 0;
+        data_start = sh && sh->index > 0 ? 1 : 0;  // a record starting at byte 0 of a later shard belongs to the shard before it
     }
     std::vector<std::string> names;
     for (auto& cc : cols) names.push_back(cc.first);
@@ -198,8 +243,18 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
     P.pred = comp.prog;
     for (int t = 0; t < comp.prog.nterms; t++) P.slot_terms[comp.prog.term_col[t]] |= 1u << t;
     P.ntiles = data_start >= n ? 0 : (uint32_t)((n + TILE - 1) / TILE);
+    P.own_end = ~0ull;
+    if (sh) {
+        P.pin0 = sh->pin0 & 1u;
+        if (!sh->is_last) {  // records that start after own_bytes are the next shard's; the tiles past that byte are never visited
+            P.own_end = sh->own_bytes;
+            if (P.ntiles) P.ntiles = (uint32_t)std::min<uint64_t>(P.ntiles, sh->own_bytes / TILE + 1);
+        }
+    }
+    P.no_fast = getenv("CPB_NO_FAST_TILE") ? 1 : 0;
+    P.subs = subs_dev;
 
-    if (P.ntiles == 0) return empty_table(names);
+    if (P.ntiles == 0) { if (sh && sh->records) *sh->records = 0; return empty_table(names); }
 
     Buf lits = dev_alloc(c, comp.lits.size() + 16);
     if (!comp.lits.empty())  // pageable source: the runtime stages it before returning
@@ -209,7 +264,7 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
 
     if (general) {
         GenResult gr;
-        general_parse(c, P, o, data_start, &gr);
+        general_parse(c, P, o, &sub, data_start, &gr);
         auto t = std::make_shared<Table>();
         t->ctx = c; t->nrows = (int64_t)gr.rows; t->first_line = line_base;
         if (gr.err_key != ~0ull) {
@@ -284,7 +339,7 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
         }
         ParseResult* hr = (ParseResult*)c->pinned_scratch(sizeof(ParseResult));
         CPB_CUDA(cudaMemcpyAsync(hr, P.result, sizeof(ParseResult), cudaMemcpyDeviceToHost, c->stream));
-        CPB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_stream(c);
         res = *hr;
         bool overflow = res.totals[1] > row_cap;
         for (int k = 0; k < nsel; k++) {
@@ -297,12 +352,19 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
         row_cap = res.totals[1] + 1;
         for (int k = 0; k < nsel; k++) data_cap[k] = res.totals[2 + k];
     }
+    if (sh) {
+        if (sh->records) *sh->records = res.totals[0];
+        if (!sh->is_last && res.eof_hit)
+            throw ArgError{CPB_ERR_ARG, "shard look-ahead too small: a record that starts in this shard runs past the end of the buffer"};
+    }
     // fold S_out into the algorithmic bytes of the scan record
     if (c->stats_on) {
         uint64_t s_out = 0;
         for (int k = 0; k < nsel; k++) s_out += res.totals[2 + k] + 4 * (res.totals[1] + 1);
         c->drain_events();
         c->stats["csv_scan"].bytes += s_out;
+        c->stats["csv_scan_tiles"].launches += P.ntiles;               // (diagnostics: tiles, and how many took general_tile)
+        c->stats["csv_scan_tiles_general"].launches += res.general_tiles;
     }
 
     auto t = std::make_shared<Table>();
@@ -323,7 +385,9 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in, uint64_t n, const cp
     for (size_t i = 0; i < cols.size(); i++) {
         Column col; col.name = cols[i].first; col.offsets = offs[col_slot[i]]; col.data = datas[col_slot[i]];
         t->cols.push_back(col);
+        t->src_field.push_back(cols[i].second);
     }
+    t->record_fields = first_nfields;
     return t;
 }
 

@@ -30,6 +30,8 @@ constexpr int GBLOCK = 256;  // chunks per block vector
 struct GenOpts {
     uint8_t delim, comment, lazy, trim;
     uint32_t T[NCLASS];  // transition vector per byte class: bits [3s, 3s+3) = next state from state s
+    uint32_t sp_bits[8]; // stand-in bytes of the multi-byte Unicode spaces (subst.cu): white space like ' '
+    const SubTable* subs;
 };
 
 __host__ __device__ inline int gen_class(uint8_t b, const GenOpts& o) {
@@ -39,6 +41,7 @@ __host__ __device__ inline int gen_class(uint8_t b, const GenOpts& o) {
     if (b == '\r') return C_R;
     if (o.comment && b == o.comment) return C_C;
     if (b == ' ' || b == '\t' || b == '\v' || b == '\f') return C_S;
+    if ((o.sp_bits[b >> 5] >> (b & 31)) & 1u) return C_S;
     return C_O;
 }
 static int gen_delta(int s, int c, bool trim) {
@@ -115,10 +118,10 @@ __global__ void g_starts(const uint8_t* __restrict__ in, uint64_t n, GenOpts o, 
 
 // Exact sequential restatement of encoding/csv readRecord with LazyQuotes / TrimLeadingSpace (single-byte comma).
 template <class Sink>
-__device__ SeqResult seq_parse_record_gen(const ByteSrc& src, uint64_t start, int delim, bool lazy, bool trim, Sink& sink) {
+__device__ SeqResult seq_parse_record_gen(const ByteSrc& src, uint64_t start, int delim, bool lazy, bool trim, const uint32_t* sp_bits, Sink& sink) {
     uint64_t pos = start;
     int f = 0;
-    auto is_sp = [](int c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r'; };
+    auto is_sp = [&](int c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r' || sub_is(sp_bits, c); };
     for (;;) {  // parseField
         sink.begin_field(f);
         if (trim) {
@@ -208,8 +211,8 @@ __global__ void g_header_kernel(const uint8_t* in, uint64_t n, GenOpts o, Header
     }
     out->truncated = 0; out->rec_start = pos; out->sample_bytes = 0; out->sample_newlines = 0; out->samp_lines = 0;
     if (pos >= n) { out->eof = 1; out->err = 0; out->nfields = 0; out->data_start = n; return; }
-    HeaderSink sink{out};
-    SeqResult r = seq_parse_record_gen(src, pos, o.delim, o.lazy, o.trim, sink);
+    HeaderSink sink{out, o.subs};
+    SeqResult r = seq_parse_record_gen(src, pos, o.delim, o.lazy, o.trim, o.sp_bits, sink);
     out->eof = 0; out->err = r.err; out->nfields = r.nfields; out->data_start = r.next;
 }
 
@@ -220,7 +223,7 @@ __global__ void g_rec_count(ParseParams P, GenOpts o, const unsigned long long* 
     if (i >= nrec) return;
     ByteSrc src{P.in, P.n, nullptr, 0, 0};
     SlowSink sink(P, false);
-    SeqResult s = seq_parse_record_gen(src, starts[first + i], (int)P.delim, o.lazy, o.trim, sink);
+    SeqResult s = seq_parse_record_gen(src, starts[first + i], (int)P.delim, o.lazy, o.trim, o.sp_bits, sink);
     Rec<MAXSEL> r;
     r.err = s.err; r.nf = s.nfields; r.present = sink.present; r.eq = sink.eq; r.slow = true; r.err_slot = 0;
     for (int k = 0; k < MAXSEL; k++) r.f[k] = (k < P.nsel && ((sink.present >> k) & 1)) ? sink.ulen[k] : 0;
@@ -244,7 +247,7 @@ __global__ void g_rec_emit(ParseParams P, GenOpts o, const unsigned long long* _
         sink.maxlen[k] = lens[(uint64_t)k * nrec + i];
         P.out_off[k][row] = off;
     }
-    seq_parse_record_gen(src, starts[first + i], (int)P.delim, o.lazy, o.trim, sink);
+    seq_parse_record_gen(src, starts[first + i], (int)P.delim, o.lazy, o.trim, o.sp_bits, sink);
 }
 __global__ void g_sentinel(ParseParams P, const uint32_t* __restrict__ offs, uint64_t nrec, uint64_t nrec_eff, uint64_t rows) {
     int k = threadIdx.x;
@@ -255,17 +258,23 @@ static inline uint32_t nblk(uint64_t n, int t) { return (uint32_t)((n + t - 1) /
 
 // Returns the raw pieces of the general parse; parse.cu turns them into a Table and error (shared logic).
 
-void general_header(Ctx* c, const uint8_t* in, uint64_t n, const cpb_reader_opts& o, HeaderOut* dev_out) {
+static void gen_subs(GenOpts& g, const Substitution* sub) {
+    if (sub && sub->table) { g.subs = sub->table->as<SubTable>(); memcpy(g.sp_bits, sub->host_table.space_bits, sizeof g.sp_bits); }
+}
+
+void general_header(Ctx* c, const uint8_t* in, uint64_t n, const cpb_reader_opts& o, const Substitution* sub, HeaderOut* dev_out) {
     GenOpts g{};
     g.delim = (uint8_t)o.delimiter; g.comment = (uint8_t)o.comment; g.lazy = o.lazy_quotes; g.trim = o.trim_leading_space;
+    gen_subs(g, sub);
     KernelTimer kt(c, "csv_header_general", 0);
     g_header_kernel<<<1, 1, 0, c->stream>>>(in, n, g, dev_out);
     CPB_CUDA(cudaGetLastError());
 }
 
-void general_parse(Ctx* c, ParseParams P, const cpb_reader_opts& o, uint64_t data_start, GenResult* out) {
+void general_parse(Ctx* c, ParseParams P, const cpb_reader_opts& o, const Substitution* sub, uint64_t data_start, GenResult* out) {
     GenOpts g{};
     g.delim = (uint8_t)o.delimiter; g.comment = (uint8_t)o.comment; g.lazy = o.lazy_quotes; g.trim = o.trim_leading_space;
+    gen_subs(g, sub);
     for (int cl = 0; cl < NCLASS; cl++) {
         uint32_t v = 0;
         for (int s = 0; s < 8; s++) v |= (uint32_t)gen_delta(s, (cl == C_C && !g.comment) ? C_O : cl, g.trim) << (3 * s);
@@ -287,7 +296,7 @@ void general_parse(Ctx* c, ParseParams P, const cpb_reader_opts& o, uint64_t dat
     exclusive_scan_u32(c, counts->as<uint32_t>(), counts->as<uint32_t>(), nchunks, tot->as<uint64_t>());
     uint64_t* hp = (uint64_t*)c->pinned_scratch(64);
     CPB_CUDA(cudaMemcpyAsync(hp, tot->p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     const uint64_t nstarts = hp[0];
     if (nstarts > 0xfffffff0ull) throw DataError{CPB_E_TOO_LARGE, -1, 0, false, "more than 2^32 records in one batch"};
     Buf starts = dev_alloc(c, (nstarts + 1) * 8);
@@ -316,7 +325,7 @@ void general_parse(Ctx* c, ParseParams P, const cpb_reader_opts& o, uint64_t dat
     }
     ParseResult* hr = (ParseResult*)c->pinned_scratch(sizeof(ParseResult));
     CPB_CUDA(cudaMemcpyAsync(hr, res->p, sizeof(ParseResult), cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     out->err_key = hr->err_key;
     const uint64_t nrec_eff = out->err_key == ~0ull ? nrec : (uint64_t)(out->err_key >> 16);  // rows before the first failing record
     out->nrec_eff = nrec_eff;
@@ -325,7 +334,7 @@ void general_parse(Ctx* c, ParseParams P, const cpb_reader_opts& o, uint64_t dat
         exclusive_scan_u32(c, lens->as<uint32_t>() + (uint64_t)k * nrec, offs->as<uint32_t>() + (uint64_t)k * (nrec + 1), nrec_eff, tots->as<uint64_t>() + 1 + k);
     uint64_t* ht = (uint64_t*)c->pinned_scratch((nsel + 1) * 8);
     CPB_CUDA(cudaMemcpyAsync(ht, tots->p, (nsel + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     out->rows = ht[0];
     for (int k = 0; k < nsel; k++) {
         if (ht[1 + k] > 0xffffffffull) throw DataError{CPB_E_TOO_LARGE, k, 0, false, "a column of this batch exceeds 4 GiB; parse the input in smaller batches"};
@@ -340,7 +349,7 @@ void general_parse(Ctx* c, ParseParams P, const cpb_reader_opts& o, uint64_t dat
         g_sentinel<<<1, 32, 0, c->stream>>>(P, offs->as<uint32_t>(), nrec, nrec_eff, out->rows);
         CPB_CUDA(cudaGetLastError());
     }
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
 }
 
 }  // namespace cpb

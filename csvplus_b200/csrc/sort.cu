@@ -140,29 +140,43 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_
 }
 
 // Stable sort of `perm` (row ids) by image words [0, words): returns the buffer holding the sorted ids.
+// Which digits are constant over the whole column (their pass would be the identity) does not depend on the order of
+// the rows: the byte histograms of ALL image words are taken from the unsorted image up front and read back with one
+// host round trip for the whole sort (round 1: one per image word).
 static Buf sort_by_image(Ctx* c, const uint64_t* image, uint32_t words, uint64_t n, uint64_t* traffic) {
     Buf permA = dev_alloc(c, n * 4), permB = dev_alloc(c, n * 4), keyA = dev_alloc(c, n * 8), keyB = dev_alloc(c, n * 8);
     iota_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(permA->as<uint32_t>(), n);
     const uint64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
     const uint32_t nblocks = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)c->sm_count * 4);
     const uint64_t tpb = (ntiles + nblocks - 1) / nblocks;
-    Buf hist = dev_alloc(c, 8 * 256 * 4), counts = dev_alloc(c, (256ull * nblocks + 1) * 4), tot = dev_alloc(c, 8);
-    uint32_t* hh = (uint32_t*)c->pinned_scratch(8 * 256 * 4);
+    Buf hist = dev_alloc(c, (size_t)words * 8 * 256 * 4), counts = dev_alloc(c, (256ull * nblocks + 1) * 4), tot = dev_alloc(c, 8);
+    CPB_CUDA(cudaMemsetAsync(hist->p, 0, (size_t)words * 8 * 256 * 4, c->stream));
+    {
+        KernelTimer kt(c, "sort_hist", n * 8 * words, (int)words);
+        for (uint32_t w = 0; w < words; w++)
+            hist8_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(image + (uint64_t)w * n, n, hist->as<uint32_t>() + (size_t)w * 8 * 256);
+        CPB_CUDA(cudaGetLastError());
+    }
+    *traffic += n * 8 * words;
+    uint32_t* hh = (uint32_t*)c->pinned_scratch((size_t)words * 8 * 256 * 4);
+    CPB_CUDA(cudaMemcpyAsync(hh, hist->p, (size_t)words * 8 * 256 * 4, cudaMemcpyDeviceToHost, c->stream));
+    sync_stream(c);
+    std::vector<uint8_t> skip((size_t)words * 8, 0);
+    for (uint32_t w = 0; w < words; w++)
+        for (int b = 0; b < 8; b++)
+            for (int v = 0; v < 256; v++) if (hh[((size_t)w * 8 + b) * 256 + v] == n) skip[(size_t)w * 8 + b] = 1;
     for (int w = (int)words - 1; w >= 0; w--) {
+        bool any = false;
+        for (int b = 0; b < 8; b++) any = any || !skip[(size_t)w * 8 + b];
+        if (!any) continue;  // the whole word is constant
         {
             KernelTimer kt(c, "sort_gather_word", n * 20);
             gather_u64_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(image + (uint64_t)w * n, permA->as<uint32_t>(), keyA->as<uint64_t>(), n);
-            CPB_CUDA(cudaMemsetAsync(hist->p, 0, 8 * 256 * 4, c->stream));
-            hist8_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(keyA->as<uint64_t>(), n, hist->as<uint32_t>());
             CPB_CUDA(cudaGetLastError());
         }
-        *traffic += n * 28;
-        CPB_CUDA(cudaMemcpyAsync(hh, hist->p, 8 * 256 * 4, cudaMemcpyDeviceToHost, c->stream));
-        CPB_CUDA(cudaStreamSynchronize(c->stream));
+        *traffic += n * 20;
         for (int b = 0; b < 8; b++) {
-            bool constant = false;
-            for (int v = 0; v < 256; v++) if (hh[b * 256 + v] == n) constant = true;
-            if (constant) continue;  // every key has the same byte here: the pass would be the identity
+            if (skip[(size_t)w * 8 + b]) continue;  // every key has the same byte here: the pass would be the identity
             KernelTimer kt(c, "radix_pass", n * 32, 3);
             radix_count_kernel<<<nblocks, RS_THREADS, 0, c->stream>>>(keyA->as<uint64_t>(), n, 8 * b, tpb, counts->as<uint32_t>());
             exclusive_scan_u32(c, counts->as<uint32_t>(), counts->as<uint32_t>(), 256ull * nblocks, tot->as<uint64_t>());
@@ -223,7 +237,7 @@ __global__ void clear_one_kernel(uint32_t* keep, uint64_t i) { keep[i] = 0; }
 static uint64_t read_u64(Ctx* c, const void* dev) {
     uint64_t* h = (uint64_t*)c->pinned_scratch(8);
     CPB_CUDA(cudaMemcpyAsync(h, dev, 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     return *h;
 }
 
@@ -262,8 +276,51 @@ Buf pack_with_widths(Ctx* c, const Table& t, const std::vector<int>& kidx, const
     return img;
 }
 
-std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std::string>& keys, bool unique, DataError* derr,
+static Buf sort_by_image(Ctx* c, const uint64_t* image, uint32_t words, uint64_t n, uint64_t* traffic);
+static void ensure_sorted_locked(Ctx* c, Index& ix) {
+    if (ix.sorted) return;
+    const uint64_t n = (uint64_t)ix.nrows;
+    Ctx* prev = c->alloc_for;
+    c->alloc_for = ix.ctx;  // what stays inside the index comes from its owner's pool
+    try {
+        uint64_t traffic = 0;
+        Buf perm = sort_by_image(c, ix.uimage->as<uint64_t>(), ix.image_words, n, &traffic);
+        Buf simg = dev_alloc(c, std::max<uint64_t>(1, (uint64_t)ix.image_words * n) * 8);
+        {
+            KernelTimer kt(c, "image_gather", (uint64_t)ix.image_words * n * 20, (int)ix.image_words);
+            for (uint32_t w = 0; w < ix.image_words; w++)
+                gather_u64_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(ix.uimage->as<uint64_t>() + (uint64_t)w * n, perm->as<uint32_t>(),
+                                                                       simg->as<uint64_t>() + (uint64_t)w * n, n);
+            CPB_CUDA(cudaGetLastError());
+        }
+        sync_stream(c);  // complete before another context (stream) can see it
+        ix.perm = perm; ix.image = simg; ix.sorted = true;
+    } catch (...) { c->alloc_for = prev; throw; }
+    c->alloc_for = prev;
+}
+void ensure_sorted(Ctx* c, Index& ix) {
+    std::lock_guard<std::mutex> lk(ix.mu);
+    ensure_sorted_locked(c, ix);
+}
+
+std::shared_ptr<Table> sorted_table(Ctx* c, Index& ix) {
+    std::lock_guard<std::mutex> lk(ix.mu);
+    if (ix.table) return ix.table;
+    ensure_sorted_locked(c, ix);
+    Ctx* prev = c->alloc_for;
+    c->alloc_for = ix.ctx;  // the sorted rows stay inside the index: they come from its owner's pool
+    try {
+        ix.table = gather_rows(c, *ix.src, ix.perm->as<uint32_t>(), ix.nrows);
+        ix.table->first_line = 0;  // iterating an Index reports 0-based rows (csvplus.go:243)
+        sync_stream(c);  // complete before another context (stream) can see it
+    } catch (...) { c->alloc_for = prev; throw; }
+    c->alloc_for = prev;
+    return ix.table;
+}
+
+std::shared_ptr<Index> build_index(Ctx* c, std::shared_ptr<Table> tp, const std::vector<std::string>& keys, bool unique, DataError* derr,
                                    bool* failed) {
+    const Table& t = *tp;
     *failed = false;
     if ((int)keys.size() > MAXKEYS) throw ArgError{CPB_ERR_UNSUPPORTED, "more than 16 index key columns"};
     auto ix = std::make_shared<Index>();
@@ -283,7 +340,7 @@ std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std
     }
     if (n == 0) {
         auto e = std::make_shared<Table>(t); e->nrows = 0;
-        ix->table = e; ix->key_width.assign(keys.size(), 0); ix->image_words = 0; ix->image = dev_alloc(c, 8);
+        ix->table = e; ix->src = e; ix->nrows = 0; ix->key_width.assign(keys.size(), 0); ix->image_words = 0; ix->image = dev_alloc(c, 8);
         for (auto& ci : ix->key_col_idx) if (ci < 0) ci = 0;
         return ix;
     }
@@ -299,19 +356,27 @@ std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std
     }
     uint32_t* hw = (uint32_t*)c->pinned_scratch(keys.size() * 4);
     CPB_CUDA(cudaMemcpyAsync(hw, wd->p, keys.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     ix->key_width.assign(hw, hw + keys.size());
     // 2. image of the unsorted rows
     uint32_t words = 0;
     Buf img = pack_with_widths(c, t, ix->key_col_idx, ix->key_width, &words);
     ix->image_words = words;
     if ((uint64_t)words * 8 > 4096) throw ArgError{CPB_ERR_UNSUPPORTED, "index keys longer than 4 KiB are not supported"};
+    // 3a. UniqueIndexOn: the duplicate check does not need the order — a probe table over the rows as they are, in which
+    //     every key must find itself.  When it passes (the usual case) the sort is left for whoever needs the order.
+    static const bool eager = getenv("CPB_EAGER_SORT") != nullptr;
+    if (unique && n >= 2 && !eager) {
+        ix->src = tp; ix->nrows = (int64_t)n; ix->uimage = img; ix->sorted = false; ix->unique = true;
+        if (!index_has_duplicates(c, *ix)) return ix;
+        // a duplicate exists: sort, so that the error names the key the reference would name (the lowest in sort order)
+        ix->unique = false; ix->sorted = true; ix->uimage = nullptr; ix->hash_src.clear(); ix->row_slots_src.clear();
+    }
     // 3. stable LSD radix sort -> permutation
     uint64_t traffic = 0;
     Buf perm = sort_by_image(c, img->as<uint64_t>(), words, n, &traffic);
-    // 4. materialise sorted rows and sorted image
-    ix->table = gather_rows(c, t, perm->as<uint32_t>(), (int64_t)n);
-    ix->table->first_line = 0;  // iterating an Index reports 0-based rows (csvplus.go:243)
+    // 4. the sorted key image; the sorted rows themselves stay virtual (src + perm) until something needs them
+    ix->src = tp; ix->perm = perm; ix->nrows = (int64_t)n;
     Buf simg = dev_alloc(c, std::max<uint64_t>(1, (uint64_t)words * n) * 8);
     {
         KernelTimer kt(c, "image_gather", (uint64_t)words * n * 20, (int)words);
@@ -321,7 +386,6 @@ std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std
         CPB_CUDA(cudaGetLastError());
     }
     ix->image = simg;
-    for (size_t k = 0; k < keys.size(); k++) ix->key_col_idx[k] = ix->table->find(keys[k]);
     // 5. uniqueness (createUniqueIndex, csvplus.go:740-756)
     if (unique && n >= 2) {
         Buf head = dev_alloc(c, n * 4), first = dev_alloc(c, 8);
@@ -337,13 +401,13 @@ std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std
             // "duplicate value while creating unique index: " + rows[i].SelectExisting(columns...).String()  (:751, :90-104)
             std::vector<std::pair<std::string, std::string>> kv;
             for (size_t k = 0; k < keys.size(); k++) {
-                const Column& col = ix->table->cols[ix->key_col_idx[k]];
+                const Column& col = sorted_table(c, *ix)->cols[ix->key_col_idx[k]];
                 uint32_t oo[2];
                 CPB_CUDA(cudaMemcpyAsync(oo, col.off() + fd, 8, cudaMemcpyDeviceToHost, c->stream));
-                CPB_CUDA(cudaStreamSynchronize(c->stream));
+                sync_stream(c);
                 std::string v(oo[1] - oo[0], '\0');
                 if (!v.empty()) CPB_CUDA(cudaMemcpyAsync(&v[0], col.bytes() + oo[0], v.size(), cudaMemcpyDeviceToHost, c->stream));
-                CPB_CUDA(cudaStreamSynchronize(c->stream));
+                sync_stream(c);
                 kv.emplace_back(keys[k], v);
             }
             std::sort(kv.begin(), kv.end());
@@ -355,6 +419,7 @@ std::shared_ptr<Index> build_index(Ctx* c, const Table& t, const std::vector<std
             return nullptr;
         }
     }
+    ix->unique = unique;
     return ix;
 }
 
@@ -371,8 +436,8 @@ static Buf compact_flags(Ctx* c, const uint32_t* flags, uint64_t n, uint32_t add
 
 void index_dup_groups(Ctx* c, Index& ix, std::vector<int64_t>& lo, std::vector<int64_t>& hi) {
     lo.clear(); hi.clear();
-    const uint64_t n = (uint64_t)ix.table->nrows;
-    if (n < 2) return;
+    const uint64_t n = (uint64_t)ix.nrows;
+    if (n < 2 || ix.unique) return;  // (a verified unique index has no duplicate group)
     Buf head = dev_alloc(c, n * 4), gs = dev_alloc(c, n * 4), ge = dev_alloc(c, n * 4);
     {
         KernelTimer kt(c, "dedup_segments", (uint64_t)ix.image_words * n * 8 + n * 12, 2);
@@ -388,15 +453,44 @@ void index_dup_groups(Ctx* c, Index& ix, std::vector<int64_t>& lo, std::vector<i
     if (ng) {
         CPB_CUDA(cudaMemcpyAsync(a.data(), los->p, ng * 4, cudaMemcpyDeviceToHost, c->stream));
         CPB_CUDA(cudaMemcpyAsync(b.data(), his->p, ng * 4, cudaMemcpyDeviceToHost, c->stream));
-        CPB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_stream(c);
     }
     lo.assign(a.begin(), a.end()); hi.assign(b.begin(), b.end());
 }
 
-// indexImpl.dedup (csvplus.go:810-867) with the resolver's choices already made on the host
-void index_dedup_apply(Ctx* c, Index& ix, const std::vector<int64_t>& keep, bool bug_compatible) {
-    const uint64_t n = (uint64_t)ix.table->nrows;
-    if (n < 2 || keep.empty()) return;  // no duplicate group: the reference returns early (:820-822)
+// indexImpl.dedup (csvplus.go:810-867) with the resolver's choices already made on the host.
+// keep[g] >= 0: sorted position of the row kept for group g; -1: the group is dropped (the resolver returned an "empty"
+// row, :845); <= -2: the resolver returned a row that is not one of the group's rows — row (-2 - keep[g]) of `repl`
+// takes the place of the group (:846 stores whatever row came back; the index is NOT re-sorted, exactly like the reference).
+__global__ void patch_ids_kernel(const uint32_t* __restrict__ pos, const int64_t* __restrict__ at, const uint32_t* __restrict__ with, uint64_t m, uint32_t* ids) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) ids[pos[at[i]]] = with[i];
+}
+
+void index_dedup_apply(Ctx* c, Index& ix, const std::vector<int64_t>& keep_in, bool bug_compatible, const Table* repl) {
+    const uint64_t n = (uint64_t)ix.nrows;
+    if (n < 2 || keep_in.empty()) return;  // no duplicate group: the reference returns early (:820-822)
+    sorted_table(c, ix);
+    std::vector<int64_t> keep = keep_in;
+    // groups answered with a replacement row keep their first position as the slot the new row goes to
+    std::vector<int64_t> rpos; std::vector<uint32_t> rid;
+    bool any_repl = false;
+    for (auto k : keep) if (k <= -2) any_repl = true;
+    if (any_repl) {
+        if (!repl) throw ArgError{CPB_ERR_ARG, "replacement rows referenced but no replacement table given"};
+        if (repl->cols.size() != ix.table->cols.size()) throw ArgError{CPB_ERR_UNSUPPORTED, "a replacement row must have the columns of the index rows"};
+        for (auto& col : ix.table->cols) if (repl->find(col.name) < 0) throw ArgError{CPB_ERR_UNSUPPORTED, "a replacement row must have the columns of the index rows"};
+        std::vector<int64_t> lo, hi;
+        index_dup_groups(c, ix, lo, hi);
+        if (lo.size() != keep.size()) throw ArgError{CPB_ERR_ARG, "keep[] does not match the duplicate groups of the index"};
+        for (size_t g = 0; g < keep.size(); g++)
+            if (keep[g] <= -2) {
+                const int64_t j = -2 - keep[g];
+                if (j >= repl->nrows) throw ArgError{CPB_ERR_ARG, "replacement row out of range"};
+                rpos.push_back(lo[g]); rid.push_back((uint32_t)(n + (uint64_t)j));
+                keep[g] = lo[g];
+            }
+    }
     Buf head = dev_alloc(c, n * 4), flag = dev_alloc(c, n * 4);
     head_flags_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>(), n, ix.image_words * 8, head->as<uint32_t>());
     singleton_flags_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(head->as<uint32_t>(), n, flag->as<uint32_t>());
@@ -407,19 +501,57 @@ void index_dedup_apply(Ctx* c, Index& ix, const std::vector<int64_t>& keep, bool
         // when a group exists and the last sorted row is a singleton it is never copied (:851-864)
         uint32_t hl[2];
         CPB_CUDA(cudaMemcpyAsync(&hl[0], head->as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
-        CPB_CUDA(cudaStreamSynchronize(c->stream));
+        sync_stream(c);
         if (hl[0] != 0) clear_one_kernel<<<1, 1, 0, c->stream>>>(flag->as<uint32_t>(), n - 1);
     }
     CPB_CUDA(cudaGetLastError());
-    uint64_t m = 0;
-    Buf ids = compact_flags(c, flag->as<uint32_t>(), n, 0, &m);
-    auto nt = gather_rows(c, *ix.table, ids->as<uint32_t>(), (int64_t)m);
+    // compaction of the kept positions (the scanned positions are needed again to patch replacement ids in)
+    Buf pos = dev_alloc(c, (n + 1) * 4), tot = dev_alloc(c, 8);
+    exclusive_scan_u32(c, flag->as<uint32_t>(), pos->as<uint32_t>(), n, tot->as<uint64_t>());
+    const uint64_t m = read_u64(c, tot->p);
+    Buf ids = dev_alloc(c, (m + 1) * 4);
+    compact_pos_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(flag->as<uint32_t>(), pos->as<uint32_t>(), ids->as<uint32_t>(), n, 0);
+    CPB_CUDA(cudaGetLastError());
+    std::shared_ptr<Table> nt;
+    if (!rpos.empty()) {
+        Buf dp = dev_alloc(c, rpos.size() * 8), dr = dev_alloc(c, rid.size() * 4);
+        CPB_CUDA(cudaMemcpyAsync(dp->p, rpos.data(), rpos.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CPB_CUDA(cudaMemcpyAsync(dr->p, rid.data(), rid.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        patch_ids_kernel<<<nblk(rpos.size(), 256), 256, 0, c->stream>>>(pos->as<uint32_t>(), dp->as<int64_t>(), dr->as<uint32_t>(), rpos.size(), ids->as<uint32_t>());
+        CPB_CUDA(cudaGetLastError());
+        // rows [0, n) = the index, rows [n, n + repl) = the replacement rows in the index's column order
+        Table rsel; rsel.ctx = c; rsel.nrows = repl->nrows;
+        for (auto& col : ix.table->cols) rsel.cols.push_back(repl->cols[repl->find(col.name)]);
+        auto both = concat_tables(c, {ix.table.get(), &rsel});
+        nt = gather_rows(c, *both, ids->as<uint32_t>(), (int64_t)m);
+        sync_stream(c);  // rpos / rid are pageable host vectors
+        // keys may have changed (even their widths): the image is rebuilt from the new rows, their order is kept
+        nt->first_line = 0;
+        ix.table = nt; ix.src = nullptr; ix.perm = nullptr; ix.nrows = (int64_t)m; ix.unique = false;
+        for (size_t k = 0; k < ix.key_cols.size(); k++) ix.key_col_idx[k] = nt->find(ix.key_cols[k]);
+        Buf wd = dev_alloc(c, ix.key_cols.size() * 4);
+        CPB_CUDA(cudaMemsetAsync(wd->p, 0, ix.key_cols.size() * 4, c->stream));
+        for (size_t k = 0; k < ix.key_cols.size() && m; k++)
+            max_len_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(nt->cols[ix.key_col_idx[k]].off(), m, wd->as<uint32_t>() + k);
+        uint32_t* hw = (uint32_t*)c->pinned_scratch(ix.key_cols.size() * 4);
+        CPB_CUDA(cudaMemcpyAsync(hw, wd->p, ix.key_cols.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        sync_stream(c);
+        ix.key_width.assign(hw, hw + ix.key_cols.size());
+        uint32_t words = 0;
+        ix.image = pack_with_widths(c, *nt, ix.key_col_idx, ix.key_width, &words);
+        ix.image_words = words;
+        ix.hash.clear(); ix.row_slots.clear();
+        return;
+    }
+    nt = gather_rows(c, *ix.table, ids->as<uint32_t>(), (int64_t)m);
     Buf simg = dev_alloc(c, std::max<uint64_t>(1, (uint64_t)ix.image_words * m) * 8);
     for (uint32_t w = 0; w < ix.image_words && m; w++)
         gather_u64_kernel<<<nblk(m, 256), 256, 0, c->stream>>>(ix.image->as<uint64_t>() + (uint64_t)w * n, ids->as<uint32_t>(),
                                                                simg->as<uint64_t>() + (uint64_t)w * m, m);
     CPB_CUDA(cudaGetLastError());
-    ix.table = nt; ix.image = simg; ix.hash.clear(); ix.row_slots.clear();
+    nt->first_line = 0;
+    ix.table = nt; ix.src = nullptr; ix.perm = nullptr; ix.nrows = (int64_t)m;
+    ix.image = simg; ix.hash.clear(); ix.row_slots.clear();
 }
 
 }  // namespace cpb

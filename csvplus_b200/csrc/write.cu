@@ -128,7 +128,7 @@ Buf table_to_csv(Ctx* c, const Table& t, const std::vector<int>& cols, const std
     exclusive_scan_u32(c, len->as<uint32_t>(), len->as<uint32_t>(), n, tot->as<uint64_t>());
     uint64_t* ht = (uint64_t*)c->pinned_scratch(8);
     CPB_CUDA(cudaMemcpyAsync(ht, tot->p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CPB_CUDA(cudaStreamSynchronize(c->stream));
+    sync_stream(c);
     const uint64_t body = *ht;
     if (body > 0xffffffffull) throw DataError{CPB_E_TOO_LARGE, -1, 0, false, "ToCsv output exceeds 4 GiB; write in smaller batches"};
     Buf out = dev_alloc(c, header.size() + body + 16);

@@ -52,6 +52,81 @@ def allgather_layout(lib, meta, ncols: int):
     return rb, bb[:ncols]
 
 
+def allgather_u64(ctx, values):
+    """cpb_allgather_u64 over the library communicator -> per-rank lists (a ctx without a communicator: one rank)"""
+    n = len(values)
+    world = ctx.lib.cpb_comm_size(ctx.h)
+    inp = (C.c_uint64 * n)(*[int(v) for v in values])
+    out = (C.c_uint64 * (n * world))()
+    st = ctx.lib.cpb_allgather_u64(ctx.h, inp, n, out)
+    if st:
+        from .api import _raise
+        _raise(st, None, ctx)
+    return [[int(out[r * n + i]) for i in range(n)] for r in range(world)]
+
+
+class ShardedParse:
+    """One file parsed by byte-range shards, one object per rank.  The three collective steps are explicit
+    so that the same code runs one-process-per-GPU (exchange = allgather_u64 / torch.distributed) and, in the tests,
+    as N simulated ranks on one GPU:
+
+        sp = ShardedParse(ctx, rank, world, file_size, read)      # read(lo, hi) -> bytes of the file
+        q = sp.step1_parity()                                     # -> exchange -> all_q
+        info = sp.step2_parse(all_q, spec=..., pred=...)          # -> exchange -> all_info
+        table, error = sp.step3_finish(all_info)                  # rows of this rank; the global DataSourceError
+
+    A record belongs to the shard in whose (lo, hi] its first byte lies; concatenating the tables in rank order gives the
+    reference's row order; the error, if any, is the reference's: first failing record, Line counted over the whole file
+    (csvplus.go:1102-1137), rows after it dropped on every rank."""
+
+    def __init__(self, ctx, rank: int, world: int, size: int, read, lookahead: int = 1 << 20, head: int = 1 << 20):
+        self.ctx, self.rank, self.world, self.size = ctx, rank, world, size
+        self.lo, self.hi = rank * size // world, (rank + 1) * size // world
+        self.is_last = rank == world - 1
+        self.buf = read(self.lo, size if self.is_last else min(size, self.hi + lookahead))
+        self.head = read(0, min(size, head)) if rank > 0 else None
+
+    def step1_parity(self) -> list:
+        from .api import csv_quote_parity
+        import numpy as np
+        own = np.frombuffer(self.buf, np.uint8)[: self.hi - self.lo]
+        return [csv_quote_parity(self.ctx, own)]
+
+    def step2_parse(self, all_q, *, spec=None, pred=None, delimiter=",", num_fields=0) -> list:
+        from .api import parse_csv, parse_csv_shard
+        pin = 0
+        for r in range(self.rank):
+            pin ^= all_q[r][0] & 1
+        hdr = True
+        base = 2
+        if self.rank > 0:
+            # the header row lives in shard 0: resolve it from the head of the file (any rank can read it) — a data error
+            # of the truncated head is not this rank's business, a header error (row 1) is everybody's
+            t, err = parse_csv(self.ctx, self.head, spec=spec, delimiter=delimiter, num_fields=num_fields)
+            if err is not None and err.Line <= 1:
+                raise err
+            fields, nf = t.parsed_from()
+            spec = list(fields.items())
+            num_fields = num_fields if num_fields != 0 else nf
+            hdr = False
+        self.table, self.records, self.err = parse_csv_shard(
+            self.ctx, self.buf, own_bytes=self.hi - self.lo, shard_index=self.rank, is_last=self.is_last, initial_parity=pin,
+            delimiter=delimiter, num_fields=num_fields, header_from_first_row=hdr, spec=spec, pred=pred)
+        self.base = base
+        return [self.records, 1 if self.err is not None else 0, self.err.Line if self.err is not None else 0]
+
+    def step3_finish(self, all_info):
+        from .api import DataSourceError
+        first_bad = next((r for r in range(self.world) if all_info[r][1]), None)
+        if first_bad is None:
+            return self.table, None
+        line = self.base + sum(all_info[r][0] for r in range(first_bad)) + all_info[first_bad][2]
+        msg = self.err.Err if self.rank == first_bad else None
+        if self.rank > first_bad:
+            self.table = self.table.slice(0, 0)  # the reference stopped before these rows
+        return self.table, (DataSourceError(line, msg) if msg is not None else DataSourceError(line, "(error raised by rank %d)" % first_bad))
+
+
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     """contiguous row range of `rank` (row-range data parallelism; concatenation in rank order = input order)"""
     return rank * total // world, (rank + 1) * total // world

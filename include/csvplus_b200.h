@@ -191,6 +191,11 @@ int cpb_index_sub(cpb_ctx* ctx, const cpb_index* ix, const cpb_str* values, int 
  * The reference's trailing-singleton loss is reproduced when bug_compatible!=0. */
 int cpb_index_dup_groups(cpb_ctx* ctx, const cpb_index* ix, int64_t* ngroups, int64_t** lo, int64_t** hi);
 int cpb_index_dedup_apply(cpb_ctx* ctx, cpb_index* ix, int64_t ngroups, const int64_t* keep, int bug_compatible);
+/* same, and keep[g] <= -2 puts row (-2 - keep[g]) of `replacements` in the place of group g: the resolver may return a
+ * row that is not one of the group's rows (csvplus.go:838-848 stores whatever row came back, without re-sorting).
+ * `replacements` must have the columns of the index rows; nullable when no keep[g] <= -2. */
+int cpb_index_dedup_apply2(cpb_ctx* ctx, cpb_index* ix, int64_t ngroups, const int64_t* keep, const cpb_table* replacements,
+                           int bug_compatible, cpb_error* err);
 void cpb_free(void* p); /* releases arrays returned by cpb_index_dup_groups / cpb_table_to_csv */
 void cpb_index_free(cpb_index* ix);
 
@@ -247,6 +252,27 @@ int cpb_allgather_u64(cpb_ctx* ctx, const uint64_t* in, int count, uint64_t* out
  * of rank q -> row_base[nranks+1], byte_base[ncols][nranks+1] */
 int cpb_allgather_layout(int nranks, int ncols, const uint64_t* meta, uint64_t* row_base, uint64_t* byte_base);
 
+/* Byte-range shards of ONE file: rank r holds the bytes [lo_r, hi_r + look-ahead) of the file, lo_0 = 0,
+ * lo_{r+1} = hi_r.  A record belongs to the shard in whose (lo, hi] its first byte lies (shard 0 also owns byte 0), so no
+ * look-behind is needed; the look-ahead must reach the end of the record that starts at hi (else CPB_ERR_ARG).
+ *   1. every rank: cpb_csv_quote_parity over its own [lo, hi)          -> q_r
+ *   2. all-gather of q (cpb_allgather_u64); initial_parity_r = XOR of q_s, s < r
+ *   3. every rank: cpb_parse_csv_shard(..., own_bytes = hi - lo, shard_index = r, is_last, initial_parity_r, ...)
+ *      -> its rows (concatenation in rank order = the reference's row order) and `records` (owned records, pre-filter)
+ *   4. all-gather of (records, failed, local line): DataSourceError.Line = base (2 with a header row, else 1) + records of
+ *      the shards before the first failing one + its local line (csvplus.go:1102-1137); later shards drop their rows.
+ * Shards after the first need the resolved header: header_from_first_row = 0, spec = (name, index) pairs, and an explicit
+ * num_fields (the count of the file's first record, or -1).  Default reader options only.  On CPB_ERR_DATA err->line is
+ * the LOCAL 0-based ordinal of the failing record among this shard's records. */
+/* of a table that cpb_parse_csv produced: the field index column `col` was read from, and the number of fields of the
+ * file's first record (-1 when the table did not come from the parser) — the resolved header for shards after the first */
+int cpb_table_col_field(const cpb_table* t, int col);
+int cpb_table_record_fields(const cpb_table* t);
+int cpb_csv_quote_parity(cpb_ctx* ctx, const void* bytes, uint64_t nbytes, int on_device, uint32_t* parity);
+int cpb_parse_csv_shard(cpb_ctx* ctx, const void* bytes, uint64_t nbytes, int on_device, uint64_t own_bytes, int shard_index, int is_last,
+                        uint32_t initial_parity, const cpb_reader_opts* opts, const cpb_header_col* spec, int nspec,
+                        const cpb_pred* filter, cpb_table** out, uint64_t* records, cpb_error* err);
+
 /* ------------------------------------------------------------------ measurement
  * Per-kernel launch records of this ctx since the last reset: name, launches, device ms (CUDA events on
  * the ctx stream) and algorithmic bytes, for the roofline JSON of bench.py. */
@@ -260,6 +286,7 @@ int cpb_stats_enable(cpb_ctx* ctx, int on);
 int cpb_stats_reset(cpb_ctx* ctx);
 int cpb_stats_get(cpb_ctx* ctx, cpb_kstat* out, int cap, int* n);
 uint64_t cpb_kernel_launches(cpb_ctx* ctx); /* total kernels this ctx has launched */
+uint64_t cpb_host_syncs(cpb_ctx* ctx);      /* blocking host waits on the ctx stream issued by the library so far */
 
 /* ------------------------------------------------------------------ synthetic data (bench / tests only)
  * Deterministic generators of SURVEY §8(d) tables, written on the GPU into a device buffer obtained from

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _default_opts(o):
-    return not (o.comment or o.lazy_quotes or o.trim_leading_space or ord(o.comma) >= 0x80)
+    return not (o.comment or o.lazy_quotes or o.trim_leading_space)
 
 
 @pytest.mark.parametrize("i", [i for i, k in enumerate(KATS) if _default_opts(k[1])])
@@ -194,7 +194,7 @@ def test_full_size_properties():
 
 # ------------------------------------------------------------------ general reader options (parse_general.cu)
 def _general_opts(o):
-    return (o.comment or o.lazy_quotes or o.trim_leading_space) and ord(o.comma) < 0x80 and (not o.comment or ord(o.comment) < 0x80)
+    return bool(o.comment or o.lazy_quotes or o.trim_leading_space)
 
 
 @pytest.mark.parametrize("i", [i for i, k in enumerate(KATS) if _general_opts(k[1])])
@@ -251,3 +251,65 @@ def test_general_options_big_and_edges():
                   orc.Opts(comment="#", lazy_quotes=True, trim_leading_space=True)):
             check_parity(data, opts=o)
             check_parity(data, opts=orc.Opts(**{**o.__dict__, "fields_per_record": -1}), assume={"x": 0, "y": 1})
+
+
+# ------------------------------------------------------------------ multi-byte reader runes (csrc/subst.cu)
+UNISPACES = ["\u0085", "\u00a0", "\u1680", "\u2000", "\u2005", "\u200a", "\u2028", "\u2029", "\u202f", "\u205f", "\u3000"]
+
+
+def test_every_kat_runs_on_the_gpu():
+    """all vectors of the restated encoding/csv table take part in the two parametrised tests above (round 1 skipped the
+    multi-byte Delimiter / CommentChar one)"""
+    assert all(_default_opts(k[1]) or _general_opts(k[1]) for k in KATS)
+    assert any(ord(k[1].comma) >= 0x80 for k in KATS)
+
+
+@pytest.mark.parametrize("comma", ["£", "€", "\u00a0", "𝄞"])
+def test_multibyte_delimiter(comma):
+    import random
+    rng = random.Random(ord(comma[0]))
+    cb = comma.encode()
+    rows = [cb.join([b"a", b"b", b"c"])]
+    for i in range(3000):
+        f = []
+        for _ in range(3):
+            kind = rng.randrange(6)
+            if kind == 0:
+                f.append(b'"q' + cb + b'uoted ""x"" ' + cb + b'"')       # the delimiter inside quotes is data
+            elif kind == 1:
+                f.append(b'"line\nbreak"')
+            elif kind == 2:
+                f.append(cb[:1] + b"x" if len(cb) > 1 else b"y")          # a lone lead byte is data
+            else:
+                f.append(bytes(rng.choice(b"abc,;\xc3\xa9 01") for _ in range(rng.randrange(0, 9))))
+        rows.append(cb.join(f))
+    data = b"\n".join(rows) + b"\n"
+    check_parity(data, opts=orc.Opts(comma=comma))
+    check_parity(data, opts=orc.Opts(comma=comma), select=["c", "a"], like={"a": "abc"})
+    check_parity(data, opts=orc.Opts(comma=comma, lazy_quotes=True, fields_per_record=-1))
+
+
+def test_multibyte_comment_and_unicode_spaces():
+    import random
+    rng = random.Random(9)
+    sp = [s.encode() for s in UNISPACES] + [b" ", b"\t"]
+    lines = [b"a,b,c"]
+    for i in range(4000):
+        if rng.random() < 0.1:
+            lines.append("€ comment, with \"quotes".encode())
+            continue
+        f = []
+        for _ in range(3):
+            lead = b"".join(rng.choice(sp) for _ in range(rng.randrange(0, 3)))
+            body = rng.choice([b"v%d" % i, b'"q,%d"' % i, b"x" + rng.choice(sp) + b"y", b"", rng.choice(sp)[:1] + b"z"])
+            f.append(lead + body)
+        lines.append(b",".join(f))
+    data = b"\n".join(lines) + b"\n"
+    o = orc.Opts(comment="€", trim_leading_space=True, fields_per_record=-1)
+    check_parity(data, opts=o)
+    check_parity(data, opts=o, select=["b"], like={"b": "x\u2028y"})
+    check_parity(data, opts=orc.Opts(comment="€", fields_per_record=-1))            # untrimmed: the spaces are data
+    check_parity(data, opts=orc.Opts(trim_leading_space=True, fields_per_record=-1))  # '€' lines are data now
+    # a delimiter that is itself multi-byte together with everything else
+    d2 = data.replace(b",", "£".encode())
+    check_parity(d2, opts=orc.Opts(comma="£", comment="€", trim_leading_space=True, lazy_quotes=True, fields_per_record=-1))
