@@ -308,6 +308,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batches", type=int, default=16)
+    ap.add_argument("--e2e-workers", type=int, default=4)
     args = ap.parse_args()
     ORD_ROWS, CUST_ROWS, PROD_ROWS, PEOPLE_ROWS, INDEX_ROWS = args.orders, args.customers, args.products, args.people, args.index_rows
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -464,8 +465,10 @@ def main():
                 t_b = cand
                 break
 
-        def index_step(tab):
-            return tab.index_on("cust_id", "prod_id")
+        def index_step(tab):  # the reference's index IS the sorted rows: materialise them inside the timed step
+            ix = tab.index_on("cust_id", "prod_id")
+            ix.table()
+            return ix
 
         ms_ix, ix_rows, st_ix, _, _ = timed(lambda: index_step(t_ix), args.steps, args.warmup)
 
@@ -526,8 +529,8 @@ def main():
         # e2e is a streaming pipeline, as a csvplus user would run large files: one uploader thread copies products,
         # customers and then the probe CSV in batches of complete records (pinned host -> device staging,
         # cpb_memcpy_h2d), so the H2D engine never idles; the main context parses / indexes the build sides as they
-        # arrive; two worker contexts (two CUDA streams) parse, join and serialise the probe batches and copy the CSV
-        # text back (cpb_table_to_csv_into) — D2H runs on the other DMA engine, concurrently with the uploads.
+        # arrive; --e2e-workers contexts (one CUDA stream each) parse, join and serialise the probe batches and copy the
+        # CSV text back (cpb_table_to_csv_into) — D2H runs on the other DMA engine, concurrently with the uploads.
         nbatch = max(2, args.e2e_batches)
         oview = h_orders.array()
         bounds = [0]
@@ -550,7 +553,8 @@ def main():
         out_cap = int(ORD_ROWS * per_row * 1.05) + (1 << 20)
         h_out = ctx.host_alloc(out_cap)
         out_slots = [(b * (out_cap // nbatch)) & ~15 for b in range(nbatch)] + [out_cap]
-        workers = [cp.Context(local), cp.Context(local)]
+        nwork = max(1, args.e2e_workers)
+        workers = [cp.Context(local) for _ in range(nwork)]
         wstreams = [torch.cuda.ExternalStream(w.stream, device=torch.device("cuda", local)) for w in workers]
         ORDER_ASSUME = [("cust_id", 1), ("prod_id", 2), ("qty", 3), ("ts", 4)]
         out_bytes = [0]
@@ -574,6 +578,7 @@ def main():
             got = [threading.Event() for _ in range(nbatch)]
             box = {}
             errs = []
+            tmarks = {}
 
             def fail(ex):
                 errs.append(ex)
@@ -587,13 +592,14 @@ def main():
                     for b in range(nbatch):
                         up.lib.cpb_memcpy_h2d(up.h, dv_orders.ptr + dv_off[b], h_orders.ptr + bounds[b], bounds[b + 1] - bounds[b])
                         got[b].set()
+                    tmarks["upload_done"] = time.perf_counter() - t_a
                 except Exception as ex:
                     fail(ex)
 
             def work(wi):
                 try:
                     w = workers[wi]
-                    for b in range(wi, nbatch, 2):
+                    for b in range(wi, nbatch, nwork):
                         got[b].wait()
                         nb = bounds[b + 1] - bounds[b]
                         if b == 0:
@@ -605,14 +611,19 @@ def main():
                         ready.wait()  # the build sides are parsed / indexed concurrently on the main context
                         if errs:
                             return
+                        w0 = time.perf_counter()
                         j = t.join(box["cidx"], "cust_id").join(box["pidx"])
                         rows_out[b] = len(j)
+                        w.sync(); w1 = time.perf_counter()
                         written[b] = j.to_csv_into(h_out, out_slots[b], *SINK_COLS, header=(b == 0))
+                        w2 = time.perf_counter()
+                        tmarks.setdefault("join_ms", []).append((w1 - w0) * 1e3); tmarks.setdefault("sink_ms", []).append((w2 - w1) * 1e3)
                         assert out_slots[b] + written[b] <= out_slots[b + 1]
                         del j, t
+                    tmarks["worker%d_done" % wi] = time.perf_counter() - t_a
                 except Exception as ex:  # surfaced by the main thread
                     fail(ex)
-            th = [threading.Thread(target=upload)] + [threading.Thread(target=work, args=(i,)) for i in range(2)]
+            th = [threading.Thread(target=upload)] + [threading.Thread(target=work, args=(i,)) for i in range(nwork)]
             for t in th:
                 t.start()
             try:
@@ -640,7 +651,10 @@ def main():
                 raise errs[0]
             out_bytes[0] = sum(written)
             if os.environ.get("BENCH_DEBUG"):
-                print("e2e step: build %.1f ms, probe+sink tail %.1f ms" % ((t_b - t_a) * 1e3, (time.perf_counter() - t_b) * 1e3), file=sys.stderr)
+                print("e2e step: build %.1f ms, probe+sink tail %.1f ms; upload done %.1f, workers done %.1f / %.1f; per batch join %.1f sink %.1f ms"
+                      % ((t_b - t_a) * 1e3, (time.perf_counter() - t_b) * 1e3, tmarks.get("upload_done", 0) * 1e3, min(v for k, v in tmarks.items() if k.startswith("worker")) * 1e3,
+                         max(v for k, v in tmarks.items() if k.startswith("worker")) * 1e3, sum(tmarks.get("join_ms", [0])) / max(1, len(tmarks.get("join_ms", [0]))),
+                         sum(tmarks.get("sink_ms", [0])) / max(1, len(tmarks.get("sink_ms", [0])))), file=sys.stderr)
             return sum(rows_out)
 
         def timed_multi(fn, steps, warmup):
@@ -652,12 +666,14 @@ def main():
             if world > 1:
                 dist.barrier()
             e0 = torch.cuda.Event(enable_timing=True)
-            ends = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ends = [torch.cuda.Event(enable_timing=True) for _ in range(1 + len(wstreams))]
             e0.record(stream)
             rows = 0
             for _ in range(steps):
                 rows = fn()
-            ends[0].record(stream); ends[1].record(wstreams[0]); ends[2].record(wstreams[1])
+            ends[0].record(stream)
+            for e, ws in zip(ends[1:], wstreams):
+                e.record(ws)
             for w in [ctx] + workers:
                 w.sync()
             torch.cuda.synchronize()
@@ -676,10 +692,10 @@ def main():
         assert first.startswith(b"name,surname,qty,product,price,ts\n"), first
         e2e = {"value": world * ORD_ROWS / (ms_e2e * 1e-3), "unit": "rows/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": h_cust.nbytes + h_prod.nbytes + h_orders.nbytes, "d2h_bytes_per_step": out_bytes[0],
-               "batches": nbatch, "host_numa_node": numa_node, "sink": "ToCsv(%s)" % ",".join(SINK_COLS),
+               "batches": nbatch, "workers": nwork, "host_numa_node": numa_node, "sink": "ToCsv(%s)" % ",".join(SINK_COLS),
                "note": "pinned host CSV -> H2D (one uploader, cpb_memcpy_h2d) -> parse/index/join/join/ToCsv on the GPU through the "
                        "public API -> D2H of the CSV text of every joined row into pinned host memory; the probe file is streamed "
-                       "in %d batches of complete records over two contexts so H2D, compute and D2H overlap" % nbatch}
+                       "in %d batches of complete records over %d contexts so H2D, compute and D2H overlap" % (nbatch, nwork)}
         ms_pe2e, _, _, _, _ = timed(lambda: parse_step(h_people), args.steps, args.warmup)
         parse_e2e = {"value": world * h_people.nbytes / (ms_pe2e * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_pe2e,
                      "h2d_bytes_per_step": h_people.nbytes}

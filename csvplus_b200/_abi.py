@@ -47,7 +47,8 @@ SYMBOLS = [
     "cpb_parse_csv", "cpb_csv_quote_parity", "cpb_parse_csv_shard", "cpb_table_col_field", "cpb_table_record_fields",
     "cpb_table_num_rows", "cpb_table_num_cols", "cpb_table_col_name", "cpb_table_find_col", "cpb_table_col_bytes",
     "cpb_table_fetch_column", "cpb_table_column_device", "cpb_table_from_host", "cpb_table_from_device",
-    "cpb_table_concat", "cpb_table_select", "cpb_table_drop", "cpb_table_filter", "cpb_table_slice", "cpb_table_free",
+    "cpb_table_concat", "cpb_table_select", "cpb_table_drop", "cpb_table_filter", "cpb_table_first_false", "cpb_table_slice",
+    "cpb_table_free",
     "cpb_index_build", "cpb_index_num_rows", "cpb_index_num_keys", "cpb_index_table", "cpb_index_find", "cpb_index_sub",
     "cpb_index_dup_groups", "cpb_index_dedup_apply", "cpb_index_dedup_apply2", "cpb_free", "cpb_index_free",
     "cpb_join", "cpb_except", "cpb_table_to_csv", "cpb_table_to_csv_device", "cpb_table_to_csv_into",
@@ -101,6 +102,7 @@ def load():
         "cpb_table_select": (i32, [vp, vp, P(Str), i32, P(vp), P(Error)]),
         "cpb_table_drop": (i32, [vp, vp, P(Str), i32, P(vp)]),
         "cpb_table_filter": (i32, [vp, vp, P(Pred), P(vp)]),
+        "cpb_table_first_false": (i32, [vp, vp, P(Pred), P(i64)]),
         "cpb_table_slice": (i32, [vp, vp, i64, i64, P(vp)]),
         "cpb_table_free": (None, [vp]),
         "cpb_index_build": (i32, [vp, vp, P(Str), i32, i32, P(vp), P(Error)]),

@@ -32,6 +32,40 @@ def _dec(b: bytes) -> str:
     return b.decode("utf-8", "surrogateescape")
 
 
+def _go_json_string(s) -> bytes:
+    """encoding/json's string encoding with HTML escaping off: `"` `\\` and control characters escaped (\\n \\r \\t, else
+    \\u00xx), U+2028 / U+2029 escaped, every invalid UTF-8 byte replaced by \\ufffd, everything else verbatim"""
+    b = _enc(s)
+    out = bytearray(b'"')
+    i, n = 0, len(b)
+    while i < n:
+        c = b[i]
+        if c < 0x80:
+            if c == 0x22: out += b'\\"'
+            elif c == 0x5C: out += b"\\\\"
+            elif c == 0x0A: out += b"\\n"
+            elif c == 0x0D: out += b"\\r"
+            elif c == 0x09: out += b"\\t"
+            elif c < 0x20: out += b"\\u00" + b"%02x" % c
+            else: out.append(c)
+            i += 1
+            continue
+        width = 2 if 0xC2 <= c <= 0xDF else 3 if 0xE0 <= c <= 0xEF else 4 if 0xF0 <= c <= 0xF4 else 0
+        chunk = b[i:i + width]
+        try:
+            ch = chunk.decode("utf-8") if width and len(chunk) == width else None
+        except UnicodeDecodeError:
+            ch = None
+        if ch is None:
+            out += b"\\ufffd"; i += 1
+        elif ch in ("\u2028", "\u2029"):
+            out += b"\\u2028" if ch == "\u2028" else b"\\u2029"; i += width
+        else:
+            out += chunk; i += width
+    out += b'"'
+    return bytes(out)
+
+
 class DataSourceError(Exception):
     """csvplus.go:1230-1238: `row %d: %s`"""
 
@@ -384,6 +418,14 @@ class Table:
         if st:
             _raise(st, None, self.ctx)
         return Table(self.ctx, h)
+
+    def first_false(self, pred: Predicate) -> int:
+        """index of the first row for which the recognisable predicate is false (len(self) if none): cpb_table_first_false"""
+        keep = []; p = pred._c(keep); out = C.c_int64()
+        st = self.ctx.lib.cpb_table_first_false(self.ctx.h, self.h, C.byref(p), C.byref(out))
+        if st:
+            _raise(st, None, self.ctx)
+        return out.value
 
     def slice(self, lo: int, hi: int) -> "Table":
         h = C.c_void_p()
@@ -771,7 +813,7 @@ class DataSource:
         for op in ops:
             kind = op[0]
             device_ok = (kind in ("select", "dropcols", "join", "except", "top", "drop")
-                         or (kind == "filter" and isinstance(op[1], Predicate) and op[1].lowerable()))
+                         or (kind in ("filter", "takewhile", "dropwhile") and isinstance(op[1], Predicate) and op[1].lowerable()))
             if device_ok:
                 if state[0] == "rows":
                     state = ("table", Table.from_rows(ctx, state[1]) if state[1] else None)
@@ -786,6 +828,12 @@ class DataSource:
                     elif kind == "except": t = t.join(op[1], *op[2], anti=True)
                     elif kind == "top": t = t.slice(0, op[1])  # note: the reference pulls one extra row
                     elif kind == "drop": t = t.slice(op[1], len(t))
+                    elif kind == "takewhile":  # csvplus.go:346-358: io.EOF at the first failing row — a later error is never met
+                        cut = t.first_false(op[1])
+                        if cut < len(t):
+                            err = None
+                        t = t.slice(0, cut)
+                    elif kind == "dropwhile": t = t.slice(t.first_false(op[1]), len(t))  # :361-374
                 except DataSourceError as e:
                     if err is None or kind in ("select", "join", "except"):
                         return ("rows", []), e
@@ -858,6 +906,30 @@ class DataSource:
         try:
             with open(name, "wb") as f:
                 self.ToCsv(f, *columns)
+        except BaseException:
+            if os.path.exists(name):
+                os.remove(name)
+            raise
+
+    def ToJSON(self, out: io.IOBase):  # csvplus.go:446-474
+        """all rows as a JSON array, formatted the way the reference's json.Encoder (SetEscapeHTML(false), no indent) writes
+        it: `[`, then per row the object with its keys sorted and a newline, a `,` before every row but the first, `]`."""
+        parts = [b"["]
+        first = [True]
+
+        def fn(row):
+            if not first[0]:
+                parts.append(b",")
+            first[0] = False
+            parts.append(b"{" + b",".join(_go_json_string(k) + b":" + _go_json_string(row[k]) for k in sorted(row, key=_enc)) + b"}\n")
+        self(fn)
+        parts.append(b"]")
+        out.write(b"".join(parts))
+
+    def ToJSONFile(self, name: str):  # csvplus.go:477-479
+        try:
+            with open(name, "wb") as f:
+                self.ToJSON(f)
         except BaseException:
             if os.path.exists(name):
                 os.remove(name)

@@ -482,6 +482,15 @@ int cpb_table_filter(cpb_ctx* h, const cpb_table* t, const cpb_pred* pred, cpb_t
     CPB_CATCH(c, nullptr)
 }
 
+int cpb_table_first_false(cpb_ctx* h, const cpb_table* t, const cpb_pred* pred, int64_t* row) {
+    if (!h || !t || !row) return CPB_ERR_ARG;
+    Ctx* c = &h->c; DeviceGuard g(c);
+    CPB_TRY(c, nullptr)
+    *row = first_false_row(c, *t->t, pred);
+    return CPB_OK;
+    CPB_CATCH(c, nullptr)
+}
+
 int cpb_table_concat(cpb_ctx* h, const cpb_table* const* parts, int nparts, cpb_table** out) {
     Ctx* c = &h->c; DeviceGuard g(c);
     CPB_TRY(c, nullptr)

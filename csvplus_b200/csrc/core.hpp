@@ -221,6 +221,7 @@ void exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, uint64_t n, u
 Column gather_column(Ctx* c, const Column& src, const uint32_t* row_ids, int64_t nout);
 std::shared_ptr<Table> gather_rows(Ctx* c, const Table& t, const uint32_t* row_ids, int64_t nout);
 std::shared_ptr<Table> filter_table(Ctx* c, const Table& t, const cpb_pred* pred);
+int64_t first_false_row(Ctx* c, const Table& t, const cpb_pred* pred);
 Column materialize(Ctx* c, const Column& col, int64_t nrows);  // view -> own compact buffers
 // rows `ids` of the index's sorted table restricted to columns `cols` (row-slot path when it pays, else gather_rows)
 std::shared_ptr<Table> gather_index_rows(Ctx* c, Index& ix, const std::vector<int>& cols, const uint32_t* ids, int64_t nout,

@@ -563,6 +563,36 @@ __global__ void compact_ids_kernel(const uint32_t* __restrict__ flags, const uin
     if (i < n && flags[i]) ids[pos[i]] = (uint32_t)i;
 }
 
+// TakeWhile / DropWhile (csvplus.go:346-374) with a recognisable predicate: the index of the first row for which the
+// predicate is FALSE (nrows when there is none) — TakeWhile is then the row range before it, DropWhile the range from it.
+__global__ void first_false_kernel(const uint32_t* __restrict__ flags, uint64_t n, unsigned long long* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i] == 0) atomicMin(out, (unsigned long long)i);
+}
+int64_t first_false_row(Ctx* c, const Table& t, const cpb_pred* pred) {
+    if (!pred) throw ArgError{CPB_ERR_ARG, "nil predicate"};
+    Compiled comp;
+    compile_pred(pred, [&](const std::string& key) { return t.find(key); }, comp);
+    const uint64_t n = (uint64_t)t.nrows;
+    if (n == 0) return 0;
+    FilterCols fc{};
+    for (int i = 0; i < comp.prog.nterms; i++) { fc.off[i] = t.cols[comp.prog.term_col[i]].off(); fc.data[i] = t.cols[comp.prog.term_col[i]].bytes(); }
+    Buf lits = dev_alloc(c, comp.lits.size() + 16);
+    if (!comp.lits.empty()) CPB_CUDA(cudaMemcpyAsync(lits->p, comp.lits.data(), comp.lits.size(), cudaMemcpyHostToDevice, c->stream));
+    Buf flags = dev_alloc(c, n * 4), out = dev_alloc(c, 8);
+    CPB_CUDA(cudaMemsetAsync(out->p, 0xff, 8, c->stream));
+    {
+        KernelTimer kt(c, "filter_like", n * 12, 2);
+        filter_flags_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(fc, comp.prog, lits->as<uint8_t>(), flags->as<uint32_t>(), n);
+        first_false_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(flags->as<uint32_t>(), n, (unsigned long long*)out->p);
+        CPB_CUDA(cudaGetLastError());
+    }
+    uint64_t* h = (uint64_t*)c->pinned_scratch(8);
+    CPB_CUDA(cudaMemcpyAsync(h, out->p, 8, cudaMemcpyDeviceToHost, c->stream));
+    sync_stream(c);
+    return *h == ~0ull ? (int64_t)n : (int64_t)*h;
+}
+
 std::shared_ptr<Table> filter_table(Ctx* c, const Table& t, const cpb_pred* pred) {
     if (!pred) throw ArgError{CPB_ERR_ARG, "nil predicate"};
     Compiled comp;

@@ -244,6 +244,7 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
     for (int t = 0; t < comp.prog.nterms; t++) P.slot_terms[comp.prog.term_col[t]] |= 1u << t;
     P.ntiles = data_start >= n ? 0 : (uint32_t)((n + TILE - 1) / TILE);
     P.own_end = ~0ull;
+    P.ds_is_start = !(sh && sh->index > 0);
     if (sh) {
         P.pin0 = sh->pin0 & 1u;
         if (!sh->is_last) {  // records that start after own_bytes are the next shard's; the tiles past that byte are never visited
@@ -251,7 +252,6 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
             if (P.ntiles) P.ntiles = (uint32_t)std::min<uint64_t>(P.ntiles, sh->own_bytes / TILE + 1);
         }
     }
-    P.no_fast = getenv("CPB_NO_FAST_TILE") ? 1 : 0;
     P.subs = subs_dev;
 
     if (P.ntiles == 0) { if (sh && sh->records) *sh->records = 0; return empty_table(names); }
@@ -363,8 +363,6 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
         for (int k = 0; k < nsel; k++) s_out += res.totals[2 + k] + 4 * (res.totals[1] + 1);
         c->drain_events();
         c->stats["csv_scan"].bytes += s_out;
-        c->stats["csv_scan_tiles"].launches += P.ntiles;               // (diagnostics: tiles, and how many took general_tile)
-        c->stats["csv_scan_tiles_general"].launches += res.general_tiles;
     }
 
     auto t = std::make_shared<Table>();

@@ -4,13 +4,12 @@
 //   classify   SWAR compares -> newline bitmap T and structural bitmap S (delimiter | newline)
 //   quotes     tiles holding a quote (or entered inside one) build the exact quote bitmap, carry the
 //              parity across tiles (look-back chain 1) and clear T inside quoted regions
-//   lines      the set bits of T are expanded, in order, into `lend` (byte position of every terminator): line i
-//              spans (lend[i-1], lend[i]].  (Round 1 also expanded every structural into a flat index; the
-//              expansion cost more instructions than the field walk below saves look-ups.)
-//   pass 1     one thread per line (blocked): walks the line's structural bits of S up to its last selected
-//              field (lines of one file have the same shape, so the lanes of a warp iterate in step), the
-//              remaining delimiters are counted with popcounts -> field extents of the selected columns, Like
-//              terms, field-count check -> (records, rows, bytes per column)
+//   index      the set bits of S are expanded, in order, into a flat shared-memory array of byte
+//              positions (sidx); the structural ordinal of every terminator goes to `ord`.
+//              Line i then spans structurals (ord[i-1], ord[i]] and field j of it is found in O(1):
+//              [sidx[ord[i-1]+j]+1, sidx[ord[i-1]+j+1])  — no per-record searching, no divergence.
+//   pass 1     one thread per line (blocked): field extents of the selected columns, Like terms,
+//              field-count check -> (records, rows, bytes per column)
 //   scan       block scan + decoupled look-back (chain 2) -> global output positions
 //   pass 2     offsets written, field bytes gathered into the column buffers
 // Lines containing quotes, or running past the window, go through the exact sequential state machine.
@@ -29,6 +28,18 @@
 //   * folding the parity verification and the any-slow vote into the block scan's barrier: 548 / 420 / 292;
 //   * 16 KiB tiles with 128-thread CTAs (-DCPB_TILE=16384 -DCPB_THREADS=128, 6 CTAs/SM): 650 / 551 / 393 against
 //     714 / 582 / 406 for the 32 KiB / 256-thread default in the same run -- the per-tile fixed costs win.
+// Round 2, measured and rejected (40 M rows; filter / orders / all-columns GB/s of input; this kernel: 712 / 582 / 408):
+//   * line-end list + per-line walk of the structural bitmap instead of the flat index (no sidx expansion):
+//     682 / 576 / 391 — the same 895 M warp-instructions per 20 M order rows: the per-line ffs walk costs what the
+//     expansion + O(1) look-ups cost, with longer dependent chains;
+//   * a separate "lean" path for quote-free regular tiles (thread owns the lines starting in its 128-byte slice, 16-bit
+//     packed scans, per-warp output staging, no row lists): parity-green but 501 / 484 / 347 — slice ownership gives
+//     threads 2 or 3 lines (19 of 32 lanes active), and fully unrolled it was 19 K instructions (instruction-cache
+//     misses), rolled it still executed more warp-instructions (755 M vs 632 M on the filter shape) than this kernel;
+//   * the tile body as a __noinline__ function: 421 / 400 / 255 — shared memory and kernel parameters are then reached
+//     through generic pointers.
+// The profile of this kernel is flat (top line 13 % of the instructions); what would move it is fewer bytes through
+// the LSU per input byte, not a different control structure.
 namespace cpb {
 
 #ifndef CPB_TILE
@@ -63,9 +74,7 @@ struct ParseResult {  // device -> host
     unsigned long long err_rows;  // rows delivered before the failing record
     unsigned long long first_row_ordinal;  // record ordinal of output row 0 (~0 if no rows)
     uint32_t fallback_tiles;      // tiles that took the dense fallback
-    uint32_t general_tiles;       // tiles that took general_tile (the rest took the lean path)
     uint32_t eof_hit;             // a record of this shard was closed by the end of the buffer, not by a terminator
-    uint32_t _pad;
 };
 
 struct ParseParams {
@@ -91,11 +100,11 @@ struct ParseParams {
     unsigned long long* words;  // [ntiles][2+nsel] totals chain: bits 63:62 status, bits 61:0 value (self-validating)
     uint32_t* ticket;
     ParseResult* result;
-    int32_t no_fast;  // 1: every tile takes general_tile (A/B runs, CPB_NO_FAST_TILE)
     const SubTable* subs;  // stand-in bytes of multi-byte reader runes (subst.cu), null when there are none
     // byte-range shards of one file (cpb_parse_csv_shard): the quote parity the buffer starts with, and the last byte
     // position at which a record may START to belong to this shard (later ones are the next shard's; ~0: no limit)
     uint32_t pin0;
+    uint32_t ds_is_start;  // data_start is itself the first byte of a record (after a header row); 0 for shards after the first
     uint64_t own_end;
 };
 
@@ -282,8 +291,8 @@ struct __align__(16) ParseSmem {
     uint32_t Tb[WIN_WORDS + 4];  // record terminators: '\n' outside quotes (+ a virtual one at EOF)
     uint32_t Sb[WIN_WORDS + 4];  // structural bytes: delimiter | terminator
     uint32_t Qb[WIN_WORDS + 4];  // quote bytes (exact; only built for tiles that contain quotes)
-    uint16_t lend[LCAP + 4];     // byte position of every terminator of the window, in order
-    uint8_t stage_pad[SCAP * 2 + LCAP * 2 - (LCAP + 4) * 2];  // pass 2 stages output over Tb..stage_pad
+    uint16_t sidx[SCAP];         // byte position of every structural, in order
+    uint16_t ord[LCAP];          // structural ordinal of every terminator, in order
     __align__(16) uint8_t lits[LITS_SMEM + 16];  // Like literals (word-wise compares read up to 7 bytes past the end)
     uint64_t mbar;
     uint64_t tile_prefix[2 + MAXSEL];
@@ -292,8 +301,7 @@ struct __align__(16) ParseSmem {
     uint64_t col_total[2 + MAXSEL];  // last tile: grand totals (records, rows, bytes per column)
     uint32_t ticket;
     uint32_t pin;
-    uint32_t nterm;              // terminators of the window that matter: those of the tile + the first of the halo
-    int32_t halo_term;           // position of the first terminator in the halo, -1 if none
+    uint32_t nstruct, nterm;     // totals of the window
 };
 
 __device__ __forceinline__ int next_set(const uint32_t* bm, int from, int lim) {
@@ -393,6 +401,8 @@ static __device__ __noinline__ void slow_record(const ParseParams& P, const Byte
     }
     SeqResult s = seq_parse_record(src, start, (int)P.delim, sink);
     o->err = s.err; o->nf = s.nfields; o->present = sink.present; o->eq = sink.eq; o->next = s.next;
+    // (shards: a record closed by the end of the buffer instead of a terminator — benign race, every writer stores 1)
+    if (!emit && s.err == K_OK && s.next >= src.n && src.n > 0 && src.get(src.n - 1) != '\n') P.result->eof_hit = 1u;
     for (int k = 0; k < P.nsel; k++) o->ulen[k] = ((sink.present >> k) & 1) ? sink.ulen[k] : 0;
 }
 
@@ -430,25 +440,24 @@ __device__ __forceinline__ void run_slow(const ParseParams& P, const ByteSrc& sr
     SlowOut so;
     slow_record(P, src, start_abs, false, nullptr, nullptr, &so);
     r.err = so.err; r.nf = so.nf; r.present = so.present; r.eq = so.eq; r.slow = true; r.err_slot = 0;
-    if (so.err == K_OK && so.next >= P.n && P.n > 0 && src.get(P.n - 1) != '\n') P.result->eof_hit = 1u;  // (benign race: every writer stores 1)
 #pragma unroll
     for (int k = 0; k < KMAX; k++) r.f[k] = k < (EXACT ? KMAX : P.nsel) ? so.ulen[k] : 0;
 }
 
-// Line `i` of the window: (lend[i-1], lend[i]].  Returns false when it is not a record.
+// Line `i` of the window through the flat structural index.  Returns false when it is not a record.
 template <int KMAX, bool EXACT, bool HP>
-__device__ __forceinline__ bool walk_line(const ParseParams& P, const ParseSmem& sm, const ByteSrc& src, const uint8_t* lits,
+__device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem& sm, const ByteSrc& src, const uint8_t* lits,
                                           bool lits_in_smem, uint64_t tile_base, int i, int nterm, int rel_n, int64_t rel_ds, bool tile_has_q,
                                           Rec<KMAX>& r) {
-    const int start = i == 0 ? 0 : (int)sm.lend[i - 1] + 1;
-    if (start >= rel_n || start < rel_ds || tile_base + (uint64_t)start > P.own_end) return false;
+    const int a = i == 0 ? -1 : (int)sm.ord[i - 1];
+    const int start = i == 0 ? 0 : (int)sm.sidx[a] + 1;
+    if (start >= rel_n || start < rel_ds) return false;
     r.present = 0; r.eq = 0; r.err = K_OK; r.err_slot = 0; r.slow = false;
     bool to_slow = i >= nterm;  // no terminator inside the window: runs past it
-    int e_nl = 0, e = 0;
+    int b = 0, e_nl = 0, e = 0;
     if (!to_slow) {
-        e_nl = sm.lend[i];
+        b = sm.ord[i]; e_nl = sm.sidx[b];
         e = e_nl;
-        if (e_nl == rel_n && rel_n < WIN && e_nl > start) P.result->eof_hit = 1u;  // closed by the virtual terminator at EOF
         if (e > start && sm.data[PRE + e - 1] == '\r') e--;  // \r\n -> \n ; trailing \r before EOF
         if (e == start) return false;                          // empty line: not a record
         if (tile_has_q && count_bits(sm.Qb, start, e_nl) != 0) to_slow = true;
@@ -456,56 +465,31 @@ __device__ __forceinline__ bool walk_line(const ParseParams& P, const ParseSmem&
     if (to_slow) {
         run_slow<KMAX, EXACT>(P, src, tile_base + start, r);
     } else {
-        // the structurals of the line, in order: delimiters, then the terminator at e_nl (always a bit of S)
-        int w = start >> 5;
-        uint32_t m = sm.Sb[w] & (0xffffffffu << (start & 31));
-        int fbeg = start, f = 0;  // field f is the one in progress, it starts at fbeg
-        bool eol = false;         // field f ended at the terminator
-#pragma unroll
-        for (int k = 0; k < KMAX; k++) r.f[k] = 0;
+        const int nf = b - a;
+        r.nf = nf;
 #pragma unroll
         for (int k = 0; k < KMAX; k++) {
-            if (k < (EXACT ? KMAX : P.nsel) && !eol) {
+            r.f[k] = 0;
+            if (k < (EXACT ? KMAX : P.nsel)) {
                 const int target = P.sel_field[k];
-                while (f < target) {  // skip the fields before the next selected one
-                    while (m == 0) m = sm.Sb[++w];
-                    const int p = (w << 5) + __ffs(m) - 1; m &= m - 1;
-                    if (p >= e_nl) { eol = true; break; }
-                    fbeg = p + 1; f++;
-                }
-                if (!eol) {
-                    while (m == 0) m = sm.Sb[++w];
-                    const int p = (w << 5) + __ffs(m) - 1; m &= m - 1;
-                    const bool last = p >= e_nl;
-                    const uint32_t len = (uint32_t)((last ? e : p) - fbeg);
-                    r.f[k] = (uint32_t)fbeg | (len << 16);
+                if (target < nf) {
+                    const int fb = target == 0 ? start : (int)sm.sidx[a + target] + 1;
+                    const int fe = target + 1 < nf ? (int)sm.sidx[a + target + 1] : e;
+                    const uint32_t len = (uint32_t)(fe - fb);
+                    r.f[k] = (uint32_t)fb | (len << 16);
                     r.present |= 1u << k;
                     uint32_t tm = HP ? P.slot_terms[k] : 0u;
                     while (tm) {
                         int t = __ffs(tm) - 1; tm &= tm - 1;
                         if (len == P.pred.term_len[t]) {
-                            const bool eq = lits_in_smem ? field_eq_smem(sm.data, PRE + fbeg, sm.lits, P.pred.term_off[t], len)
-                                                         : bytes_eq(sm.data + PRE + fbeg, lits + P.pred.term_off[t], len);
+                            const bool eq = lits_in_smem ? field_eq_smem(sm.data, PRE + fb, sm.lits, P.pred.term_off[t], len)
+                                                         : bytes_eq(sm.data + PRE + fb, lits + P.pred.term_off[t], len);
                             if (eq) r.eq |= 1u << t;  // (inline: an out-of-line compare measured 708 vs 729 GB/s)
                         }
                     }
-                    if (last) eol = true; else { fbeg = p + 1; f++; }
                 }
             }
         }
-        // field count = index of the last field + 1: the delimiters not walked are counted, not visited
-        int nf = f + 1;
-        if (!eol && P.expect_fields > 0) {
-            const int we = e_nl >> 5;
-            const uint32_t em = (1u << (e_nl & 31)) - 1u;
-            if (w == we) nf += __popc(m & em);
-            else {
-                nf += __popc(m);
-                for (int ww = w + 1; ww < we; ww++) nf += __popc(sm.Sb[ww]);
-                nf += __popc(sm.Sb[we] & em);
-            }
-        }
-        r.nf = nf;
     }
     finish_record<KMAX, EXACT, HP>(P, r);
     return true;
@@ -590,663 +574,33 @@ __device__ __forceinline__ void lookback_totals_w0(const unsigned long long* wor
     if (lane < NP) sm.tile_prefix[lane] = excl;
 }
 
-// Everything after the classification of a tile, for any input: quotes, parity chains, lines, pass 1, block scan +
-// look-back, pass 2.  Tiles the lean path (fast_tile below) declines come here; out of line so that the hot loop of
-// regular inputs does not carry its code.
-template <int KMAX, bool EXACT, bool HP>
-static __device__ __noinline__ void general_tile(const ParseParams& P, ParseSmem& sm, const uint32_t tile, const uint64_t tile_base,
-                                                 const int64_t rel_n64, const bool hasq, const uint8_t* lits, const bool lits_in_smem) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NP = 2 + (EXACT ? KMAX : P.nsel);
-    const uint32_t Q4 = 0x22222222u;
-    const int rel_n = rel_n64 < WIN ? (int)rel_n64 : WIN;  // also the limit of valid window bytes
-    const bool eof_in_win = rel_n64 < WIN;
-    const int64_t rel_ds = (int64_t)P.data_start - (int64_t)tile_base;
-    const uint4* d4 = reinterpret_cast<const uint4*>(sm.data + PRE);
-    uint32_t tile_par = 0;
-    if (hasq) {
-        uint16_t* Q16 = reinterpret_cast<uint16_t*>(sm.Qb);
-        for (int v = tid; v < WIN / 16; v += THREADS) {
-            uint4 x = d4[v];
-            Q16[v] = (uint16_t)flags16(eq_flags(x.x, Q4), eq_flags(x.y, Q4), eq_flags(x.z, Q4), eq_flags(x.w, Q4));
+// Byte-range shards (not the file's last): the tile that holds own_end keeps only the lines that start at or before it
+// — starts ascend with the line index, so that is a prefix — and the tile that sees the end of the buffer reports
+// whether the line closed by the virtual terminator there is one of this shard's records (look-ahead too small).
+// Cold and out of line: the hot per-line code carries none of it.
+static __device__ __noinline__ int shard_tile_tail(const ParseParams& P, const ParseSmem& sm, uint32_t tile, uint64_t tile_base, int i0, int m_last,
+                                                   int nterm, int rel_n, int64_t rel_ds) {
+    int m_last_v = m_last;
+    if (tile == P.ntiles - 1) {
+        const int64_t rel_oe = (int64_t)(P.own_end - tile_base);
+        int lo = i0 - 1, hi = m_last;  // invariant: line lo starts <= rel_oe (or lo = i0 - 1); lines after hi start > rel_oe
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            const int st = mid == 0 ? 0 : (int)sm.sidx[sm.ord[mid - 1]] + 1;
+            if (st <= rel_oe) lo = mid; else hi = mid - 1;
         }
-        __syncthreads();
-        uint32_t par = 0;
-        for (int w = tid; w < TILE_WORDS; w += THREADS) par ^= __popc(sm.Qb[w]);
-        tile_par = __syncthreads_count(par & 1) & 1;
+        m_last_v = lo;
     }
-    // ---- chain 1: quote parity at the tile start.  The tile's own parity is published at once; a tile
-    // without quotes does not wait for its predecessors here: it proceeds assuming it starts outside
-    // quotes and verifies that after pass 1 (the rare miss redoes the tile from `retry`).
-    if (tid == 0) st_release_u32(&P.st1[tile], tile == 0 ? (2u | ((P.pin0 ^ tile_par) << 2)) : (1u | (tile_par << 2)));
-    uint32_t pin = tile == 0 ? P.pin0 : 0;
-    bool pin_known = tile == 0;
-    if (hasq && !pin_known) {
-        if (warp == 0) {
-            const uint32_t pv = lookback_parity_w0(P.st1, tile);
-            if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
-        }
-        __syncthreads();
-        pin = sm.pin;
-        pin_known = true;
+    if (rel_n < WIN && threadIdx.x == 0 && nterm >= 1) {
+        const int il = nterm - 1;
+        const int st = il == 0 ? 0 : (int)sm.sidx[sm.ord[il - 1]] + 1;
+        if (il >= i0 && il <= m_last_v && st < rel_n && st >= rel_ds && (int)sm.sidx[sm.ord[il]] == rel_n) P.result->eof_hit = 1u;
     }
-retry:
-    if (hasq || pin) {
-        // in-quote mask by prefix-XOR of the quote bitmap; terminators are newlines outside quotes
-        uint32_t carry = pin;
-        for (int r0 = 0; r0 < WIN_WORDS; r0 += THREADS) {
-            int w = r0 + tid;
-            uint32_t q = (w < WIN_WORDS && hasq) ? sm.Qb[w] : 0;
-            uint32_t px = q; px ^= px << 1; px ^= px << 2; px ^= px << 4; px ^= px << 8; px ^= px << 16;
-            uint32_t bal = __ballot_sync(0xffffffffu, px >> 31);
-            uint32_t before = __popc(bal & lanemask_lt()) & 1;
-            if (lane == 0) sm.wpar[warp] = __popc(bal) & 1;
-            __syncthreads();
-            uint32_t c = carry, tot = 0;
-            for (int i = 0; i < THREADS / 32; i++) { if (i < warp) c ^= sm.wpar[i]; tot ^= sm.wpar[i]; }
-            uint32_t cin = c ^ before;
-            uint32_t iq = (px ^ q) ^ (0u - cin);
-            if (w < WIN_WORDS) sm.Tb[w] &= ~iq;  // (Sb keeps quoted newlines/delimiters: only lines with quotes see them)
-            carry ^= tot;
-            __syncthreads();
-        }
-    }
-    // a virtual terminator at EOF closes a last line that has no newline
-    if (eof_in_win && tid == 0) { sm.Tb[rel_n >> 5] |= 1u << (rel_n & 31); sm.Sb[rel_n >> 5] |= 1u << (rel_n & 31); }
-    if (eof_in_win) __syncthreads();
-
-    // ---- line ends: the terminators of the tile, in order, + the first one of the halo
-    uint4 tw = reinterpret_cast<const uint4*>(sm.Tb)[tid];
-    {
-        const uint32_t tws[4] = {tw.x, tw.y, tw.z, tw.w};
-        const uint32_t ct = __popc(tw.x) + __popc(tw.y) + __popc(tw.z) + __popc(tw.w);
-        const uint32_t inc = warp_incl_scan(ct);
-        if (lane == 31) sm.wtot[0][warp] = inc;
-        if (warp == 0) {  // 64 halo words: the line that starts last in the tile ends at the first terminator there
-            const uint32_t h0 = sm.Tb[TILE_WORDS + lane], h1 = sm.Tb[TILE_WORDS + 32 + lane];
-            const uint32_t b0 = __ballot_sync(0xffffffffu, h0 != 0), b1 = __ballot_sync(0xffffffffu, h1 != 0);
-            int pos = -1;
-            if (b0) { const int l = __ffs(b0) - 1; pos = (TILE_WORDS + l) * 32 + __ffs(__shfl_sync(0xffffffffu, h0, l)) - 1; }
-            else if (b1) { const int l = __ffs(b1) - 1; pos = (TILE_WORDS + 32 + l) * 32 + __ffs(__shfl_sync(0xffffffffu, h1, l)) - 1; }
-            if (lane == 0) sm.halo_term = pos;
-        }
-        __syncthreads();
-        uint32_t tc = inc - ct, tile_tot = 0;
-#pragma unroll
-        for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) tc += t; tile_tot += t; }
-        // the total is known before the expansion: a window with more lines than `lend` holds skips it (dense fallback)
-        const bool fits = tile_tot + 1 <= (uint32_t)LCAP;
-        if (fits) {
-#pragma unroll
-            for (int j = 0; j < WPT; j++) {
-                uint32_t tm = tws[j];
-                const int pos0 = (tid * WPT + j) * 32;
-                while (tm) {
-                    const int bpos = __ffs(tm) - 1; tm &= tm - 1;
-                    sm.lend[tc++] = (uint16_t)(pos0 + bpos);
-                }
-            }
-        }
-        if (tid == 0) {
-            const int ht = sm.halo_term;
-            if (fits && ht >= 0) sm.lend[tile_tot] = (uint16_t)ht;
-            sm.nterm = fits ? tile_tot + (ht >= 0 ? 1u : 0u) : (uint32_t)LCAP + 1u;
-            sm.wpar[0] = tile_tot;  // terminators of the tile proper (needed below)
-        }
-        __syncthreads();
-    }
-    const int nterm = (int)sm.nterm;
-    const bool flat_ok = sm.nterm <= LCAP;
-    const bool first_owned = tile_base == 0 || (sm.data[PRE - 1] == '\n' && pin == 0);
-    // lines 1..m start inside the tile proper (terminator i-1 at position <= TILE-2); line 0 iff first_owned
-    const int m_last = (int)sm.wpar[0] - (int)((sm.Tb[TILE_WORDS - 1] >> 31) & 1);
-    const int i0 = first_owned ? 0 : 1;
-    const int nown = m_last - i0 + 1;
-    const int L = (nown + THREADS - 1) / THREADS;
-    ByteSrc src{P.in, P.n, sm.data + PRE, tile_base, tile_base + (uint64_t)rel_n};
-
-    // record-start bits of this thread's 4 words (dense fallback only)
-    uint32_t rs[WPT] = {0, 0, 0, 0};
-    if (!flat_ok) {
-        uint32_t prev = tid == 0 ? (first_owned && tile_base > 0 ? 0x80000000u : 0u) : sm.Tb[tid * WPT - 1];
-        rs[0] = (tw.x << 1) | (prev >> 31);
-        rs[1] = (tw.y << 1) | (tw.x >> 31);
-        rs[2] = (tw.z << 1) | (tw.y >> 31);
-        rs[3] = (tw.w << 1) | (tw.z >> 31);
-#pragma unroll
-        for (int j = 0; j < WPT; j++) {
-            const int64_t b0 = (int64_t)(tid * WPT + j) * 32;
-            uint32_t keep = 0xffffffffu;
-            if (rel_ds > b0) keep = rel_ds >= b0 + 32 ? 0u : (0xffffffffu << (rel_ds - b0));
-            if (rel_n64 < b0 + 32) keep &= rel_n64 <= b0 ? 0u : (0xffffffffu >> (32 - (rel_n64 - b0)));
-            rs[j] &= keep;
-            if (rel_ds >= b0 && rel_ds < b0 + 32 && rel_ds < rel_n64) rs[j] |= 1u << (rel_ds - b0);
-        }
-        if (tid == 0 && tile_base == 0 && rel_ds <= 0) rs[0] |= 1u;  // file start
-        if (tid == 0) atomicAdd(&P.result->fallback_tiles, 1u);
-    }
-
-    // ---- pass 1: count records / surviving rows / bytes per column
-    uint32_t nrec = 0, nrow = 0, cb[KMAX];
-    uint32_t my_err = 0xffffffffu;  // (local record idx << 16) | kind << 8 | slot
-    uint32_t err_rows_local = 0, first_surv_rec = 0;
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) cb[k] = 0;
-    auto account = [&](const Rec<KMAX>& r) -> bool {
-        bool survived = false;
-        if (r.err != K_OK) {
-            if (my_err == 0xffffffffu) { my_err = (nrec << 16) | ((uint32_t)r.err << 8) | (uint32_t)r.err_slot; err_rows_local = nrow; }
-        } else if (!HP || eval_pred(P.pred, r.eq)) {
-            if (nrow == 0) first_surv_rec = nrec;
-            nrow++;
-            survived = true;
-#pragma unroll
-            for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) cb[k] += r.slow ? r.f[k] : (r.f[k] >> 16);
-        }
-        nrec++;
-        return survived;
-    };
-    // pass-1 results of the first RC lines of a thread stay in registers so that pass 2 only writes
-    constexpr int RC = KMAX <= 4 ? 6 : (KMAX <= 8 ? 3 : 1);
-    uint32_t cf[RC][KMAX];
-    uint32_t cmask = 0;
-    bool any_slow = false;
-    if (flat_ok) {
-#pragma unroll
-        for (int q = 0; q < RC; q++) {
-#pragma unroll
-            for (int k = 0; k < KMAX; k++) cf[q][k] = 0;
-            const int i = i0 + tid * L + q;
-            if (q < L && i <= m_last) {
-                Rec<KMAX> r;
-                if (walk_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
-                    const bool surv = account(r);
-                    if (r.slow) any_slow = true;
-                    else if (surv) {
-                        cmask |= 1u << q;
-#pragma unroll
-                        for (int k = 0; k < KMAX; k++) cf[q][k] = r.f[k];
-                    }
-                }
-            }
-        }
-        for (int q = RC; q < L; q++) {
-            const int i = i0 + tid * L + q;
-            if (i > m_last) break;
-            Rec<KMAX> r;
-            if (walk_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
-        }
-    } else {
-#pragma unroll 1
-        for (int j = 0; j < WPT; j++) {
-            uint32_t m = rs[j];
-            while (m) {
-                int b = __ffs(m) - 1; m &= m - 1;
-                Rec<KMAX> r;
-                if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, (tid * WPT + j) * 32 + b, rel_n, r)) account(r);
-            }
-        }
-    }
-    if (!pin_known) {  // verify the optimistic assumption "this tile starts outside quotes"
-        if (warp == 0) {
-            const uint32_t pv = lookback_parity_w0(P.st1, tile);
-            if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
-        }
-        __syncthreads();
-        pin = sm.pin;
-        pin_known = true;
-        if (pin) goto retry;
-    }
-    // staged output (coalesced stores) needs every row of the tile cached and on the fast path
-    const bool staged_pre = !__syncthreads_or(any_slow) && flat_ok && L <= RC;
-    // ---- block scan of (records | rows << 16, bytes[k])
-    uint32_t v0 = nrec | (nrow << 16);
-    uint32_t i0s = warp_incl_scan(v0);
-    uint32_t ik[KMAX];
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) ik[k] = warp_incl_scan(cb[k]);
-    if (lane == 31) {
-        sm.wtot[0][warp] = i0s;
-#pragma unroll
-        for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) sm.wtot[1 + k][warp] = ik[k];
-    }
-    __syncthreads();
-    uint32_t ex0 = i0s - v0, tot0 = 0;
-    uint32_t exk[KMAX], totk[KMAX];
-#pragma unroll
-    for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) ex0 += t; tot0 += t; }
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-        exk[k] = 0; totk[k] = 0;
-        if (k < (EXACT ? KMAX : P.nsel)) {
-            exk[k] = ik[k] - cb[k];
-#pragma unroll
-            for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[1 + k][i]; if (i < warp) exk[k] += t; totk[k] += t; }
-        }
-    }
-    const bool staged = staged_pre && (tot0 >> 16) <= (uint32_t)LCAP;
-    // ---- chain 2: global prefix of (records, rows, bytes[k])
-    {
-        unsigned long long mine = 0;  // component `tid` of this tile's totals
-        if (tid == 0) mine = tot0 & 0xffffu;
-        else if (tid == 1) mine = tot0 >> 16;
-#pragma unroll
-        for (int k = 0; k < KMAX; k++) if (tid == 2 + k) mine = totk[k];
-        unsigned long long* wt = P.words + (uint64_t)tile * NP;
-        if (tile == 0) {
-            if (tid < NP) { st_relaxed_u64((uint64_t*)(wt + tid), LB_INCL | mine); sm.tile_prefix[tid] = 0; }
-            __syncthreads();
-        } else {
-            if (tid < NP) st_relaxed_u64((uint64_t*)(wt + tid), LB_AGG | mine);
-            if (warp == 0) {
-                lookback_totals_w0<KMAX>(P.words, tile, NP, sm);
-                if (lane < NP) st_relaxed_u64((uint64_t*)(wt + lane), LB_INCL | (sm.tile_prefix[lane] + mine));
-            }
-            __syncthreads();
-        }
-        if (tile == P.ntiles - 1 && tid < NP) {  // totals + end-of-column sentinels
-            const unsigned long long total = sm.tile_prefix[tid] + mine;
-            P.result->totals[tid] = total;
-            sm.col_total[tid] = total;
-        }
-        if (tile == P.ntiles - 1) {
-            __syncthreads();
-            const unsigned long long rows = sm.col_total[1];
-            if (tid >= 2 && tid < NP && rows <= P.row_cap) P.out_off[tid - 2][rows] = (uint32_t)sm.col_total[tid];
-        }
-    }
-
-    // ---- pass 2: write offsets, gather field bytes
-    {
-        const uint64_t rec0 = sm.tile_prefix[0] + (ex0 & 0xffffu);
-        uint64_t row = sm.tile_prefix[1] + (ex0 >> 16);
-        if (my_err != 0xffffffffu) {
-            unsigned long long key = ((rec0 + (my_err >> 16)) << 16) | (my_err & 0xffffu);
-            atomicMin(&P.result->err_key, key);
-            atomicMin(&P.result->err_rows, (unsigned long long)(row + err_rows_local));
-        }
-        if (staged) {
-            // Tb|Sb|Qb|lend|stage_pad are dead once pass 1 has cached every row: their 33 KB hold, per column, the
-            // row list (source extent, destination offset) and a staging buffer, so that rows are copied by
-            // all threads evenly and HBM sees full, aligned 16-byte stores.
-            uint32_t* ost = reinterpret_cast<uint32_t*>(sm.Tb);  // [LCAP + 4] destination offsets of the tile's rows
-            uint32_t* wl = ost + (LCAP + 4);                      // [LCAP]     beg | len << 16 of the field
-            uint8_t* stage = reinterpret_cast<uint8_t*>(wl + LCAP);
-            constexpr uint32_t REGION = 3 * (WIN_WORDS + 4) * 4 + SCAP * 2 + LCAP * 2;
-            constexpr uint32_t CH = ((REGION - (2 * LCAP + 4) * 4) / 16) * 16;
-            const uint32_t tile_rows = tot0 >> 16;
-            const uint64_t row_base = sm.tile_prefix[1];
-            const uint32_t osh = (uint32_t)(row_base & 3);
-            if (nrow != 0 && row == 0) P.result->first_row_ordinal = rec0 + first_surv_rec;
-            // (a run-time column loop -- one copy of the staging code instead of KMAX -- measured slower: 679 vs 736 GB/s)
-#pragma unroll
-            for (int k = 0; k < KMAX; k++) {
-                if (k < (EXACT ? KMAX : P.nsel)) {
-                    const uint64_t dbase = sm.tile_prefix[2 + k];
-                    uint32_t myf[RC], exk_k = 0, totk_k = 0;
-#pragma unroll
-                    for (int kk = 0; kk < KMAX; kk++) if (kk == k) { exk_k = exk[kk]; totk_k = totk[kk]; }
-#pragma unroll
-                    for (int q = 0; q < RC; q++) {
-                        myf[q] = 0;
-#pragma unroll
-                        for (int kk = 0; kk < KMAX; kk++) if (kk == k) myf[q] = cf[q][kk];
-                    }
-                    {
-                        uint32_t j = ex0 >> 16, run = exk_k;
-#pragma unroll
-                        for (int q = 0; q < RC; q++)
-                            if ((cmask >> q) & 1) { ost[osh + j] = (uint32_t)(dbase + run); wl[j] = myf[q]; j++; run += myf[q] >> 16; }
-                    }
-                    __syncthreads();
-                    // ---- offsets of this tile's rows
-                    {
-                        uint32_t* gout = P.out_off[k] + (row_base - osh);
-                        const uint64_t rows_ok = P.row_cap > row_base ? P.row_cap - row_base : 0;  // rows of this tile that fit
-                        const uint32_t lim_e = osh + (uint32_t)(tile_rows < rows_ok ? tile_rows : rows_ok);
-                        for (uint32_t e = tid * 4; e < lim_e; e += THREADS * 4)
-                            if (e >= osh && e + 4 <= lim_e) *reinterpret_cast<uint4*>(gout + e) = *reinterpret_cast<const uint4*>(ost + e);
-                        if (tid < 8) {  // partial first / last vector: one element per lane
-                            const uint32_t tv0 = lim_e & ~3u;
-                            const uint32_t x = tid < 4 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 4);
-                            const bool head = tid < 4 && osh != 0;
-                            const bool tail = tid >= 4 && (lim_e & 3u) != 0 && !(tv0 == 0 && osh != 0);
-                            if ((head || tail) && x >= osh && x < lim_e) gout[x] = ost[x];
-                        }
-                    }
-                    // ---- field bytes
-                    const uint32_t B = totk_k;
-                    const uint32_t r16 = (uint32_t)(dbase & 15);
-                    const uint64_t room = P.data_cap[k] > dbase ? P.data_cap[k] - dbase : 0;
-                    const uint32_t hi_ok = r16 + (uint32_t)(B < room ? B : room);  // shifted local end of writable bytes
-                    uint8_t* gbase = P.out_data[k] + (dbase - r16);
-                    for (uint32_t c0 = 0; c0 < r16 + B; c0 += CH) {
-                        for (uint32_t j = tid; j < tile_rows; j += THREADS) {
-                            const uint32_t f = wl[j], len = f >> 16;
-                            const uint32_t st = ost[osh + j] - (uint32_t)dbase + r16;  // shifted tile-local start
-                            const uint32_t lo = st > c0 ? st : c0, hi = st + len < c0 + CH ? st + len : c0 + CH;
-                            const uint8_t* sp = sm.data + PRE + (f & 0xffffu) - st;
-                            for (uint32_t x = lo; x < hi; x++) stage[x - c0] = sp[x];  // (word-wise copies measured slower)
-                        }
-                        __syncthreads();
-                        const uint32_t cend = c0 + CH < r16 + B ? c0 + CH : r16 + B;
-                        for (uint32_t x0 = c0 + tid * 16; x0 < cend; x0 += THREADS * 16)
-                            if (x0 >= r16 && x0 + 16 <= hi_ok) *reinterpret_cast<uint4*>(gbase + x0) = *reinterpret_cast<const uint4*>(stage + (x0 - c0));
-                        // the (at most two) partial vectors at the column's first and last byte: one byte per lane
-                        if (tid < 32) {
-                            const uint32_t tv0 = hi_ok & ~15u;
-                            const uint32_t x = tid < 16 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 16);
-                            const bool head = tid < 16 && c0 == 0 && r16 != 0;
-                            const bool tail = tid >= 16 && (hi_ok & 15u) != 0 && tv0 >= c0 && tv0 < cend && !(tv0 == 0 && r16 != 0);
-                            if ((head || tail) && x >= r16 && x < hi_ok) gbase[x] = stage[x - c0];
-                        }
-                        __syncthreads();
-                    }
-                    __syncthreads();
-                }
-            }
-        } else if (nrow != 0) {
-            uint64_t off[KMAX];
-#pragma unroll
-            for (int k = 0; k < KMAX; k++) off[k] = k < (EXACT ? KMAX : P.nsel) ? sm.tile_prefix[2 + k] + exk[k] : 0;
-            uint32_t rec_local = 0;
-            auto emit = [&](const Rec<KMAX>& r, uint64_t start_abs) {
-                if (r.err != K_OK || (HP && !eval_pred(P.pred, r.eq))) { rec_local++; return; }
-                if (row == 0) P.result->first_row_ordinal = rec0 + rec_local;
-                const bool row_ok = row < P.row_cap;
-                if (r.slow) {
-                    uint64_t dst_off[MAXSEL];
-                    uint32_t maxlen[MAXSEL];
-                    SlowOut so;
-#pragma unroll
-                    for (int k = 0; k < KMAX; k++) { dst_off[k] = off[k]; maxlen[k] = r.f[k]; }
-                    slow_record(P, src, start_abs, true, dst_off, maxlen, &so);
-                }
-#pragma unroll
-                for (int k = 0; k < KMAX; k++) {
-                    if (k < (EXACT ? KMAX : P.nsel)) {
-                        uint32_t len = r.slow ? r.f[k] : (r.f[k] >> 16);
-                        if (row_ok) P.out_off[k][row] = (uint32_t)off[k];
-                        if (!r.slow && off[k] + len <= P.data_cap[k]) {
-                            const uint8_t* s = sm.data + PRE + (r.f[k] & 0xffffu);
-                            uint8_t* d = P.out_data[k] + off[k];
-                            for (uint32_t i = 0; i < len; i++) d[i] = s[i];
-                        }
-                        off[k] += len;
-                    }
-                }
-                row++; rec_local++;
-            };
-            if (flat_ok) {
-                for (int q = 0; q < L; q++) {
-                    const int i = i0 + tid * L + q;
-                    if (i > m_last) break;
-                    Rec<KMAX> r;
-                    if (walk_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
-                        emit(r, tile_base + (i == 0 ? 0 : (uint64_t)sm.lend[i - 1] + 1));
-                }
-            } else {
-#pragma unroll 1
-                for (int j = 0; j < WPT; j++) {
-                    uint32_t m = rs[j];
-                    while (m) {
-                        int b = __ffs(m) - 1; m &= m - 1;
-                        const int ws = (tid * WPT + j) * 32 + b;
-                        Rec<KMAX> r;
-                        if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, ws, rel_n, r)) emit(r, tile_base + ws);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------ the lean path: regular tiles of regular inputs
-// An interior tile (not the first, no end of input inside its window) without a single quote whose lines all are
-// plain records — terminated inside the window, right number of fields, every selected column present — needs none
-// of the machinery above.  fast_tile works such a tile with a fraction of the instructions; the moment anything
-// else shows up it returns false BEFORE it has published or written anything and the tile goes to general_tile
-// (correctness never depends on the lean path taking a tile).
-//   lines     thread t owns the lines that START in its 128-byte slice: their starts follow from the terminator
-//             bitmap directly (no scan, no line list), their number is small (<= RC, else the tile is declined)
-//   fields    per line: walk the structural bits up to the last selected field, count the rest with popcounts
-//   scan      16-bit packed block scan (a tile's totals are < 64 Ki): (records|rows), column bytes two per word
-//   output    per warp: its rows are consecutive, so for each column the warp stages the offsets and the bytes of
-//             its rows in a private piece of shared memory and writes them out coalesced — no block barrier after
-//             the look-back, no per-tile row lists
-constexpr int FT_WSTAGE = 3072;   // bytes of one column a warp may stage (+16 for the alignment shift)
-constexpr int FT_WROWS = 192;     // rows a warp may own (32 lanes x RC <= 6)
-struct FastWarpBuf { uint32_t off[FT_WROWS]; __align__(16) uint8_t stage[FT_WSTAGE + 16]; };
-static_assert(sizeof(FastWarpBuf) * (THREADS / 32) <= 3 * (WIN_WORDS + 4) * 4 + (LCAP + 4) * 2 + SCAP * 2 + LCAP * 2 - (LCAP + 4) * 2,
-              "the per-warp buffers overlay Tb..stage_pad");
-
-__device__ __forceinline__ int ft_next_bit(const uint32_t* bm, int from) {  // first set bit at >= from, WIN if none
-    int w = from >> 5;
-    uint32_t m = bm[w] & (0xffffffffu << (from & 31));
-    while (m == 0) {
-        if (++w >= WIN_WORDS) return WIN;
-        m = bm[w];
-    }
-    return (w << 5) + __ffs(m) - 1;
-}
-
-template <int K, bool HP>
-__device__ __forceinline__ bool fast_tile(const ParseParams& P, ParseSmem& sm, const uint32_t tile, const uint64_t tile_base,
-                                          const uint8_t* lits, const bool lits_in_smem) {
-    constexpr int RC = K <= 4 ? 6 : (K <= 6 ? 4 : 3);
-    constexpr int NW = 1 + (K + 1) / 2;  // packed scan words
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    static_assert(TILE / THREADS == 128, "a thread owns four bitmap words");
-    uint32_t cf[RC][K];
-    uint32_t cmask = 0, nrec = 0, nrow = 0, first_surv = 0, cb[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) cb[k] = 0;
-    bool irregular = false;
-    // ---- the starts of the lines that begin in my 128-byte slice: bit p of ls = "a line starts at slice byte p",
-    // i.e. the byte before it is a terminator (for the very first byte of the tile: the last byte of the tile before)
-    int st[RC + 1];
-    {
-        const uint4 tw = reinterpret_cast<const uint4*>(sm.Tb)[tid];
-        const uint32_t prev = tid == 0 ? (sm.data[PRE - 1] == '\n' ? 0x80000000u : 0u) : sm.Tb[tid * 4 - 1];
-        uint32_t m0 = (tw.x << 1) | (prev >> 31), m1 = (tw.y << 1) | (tw.x >> 31), m2 = (tw.z << 1) | (tw.y >> 31), m3 = (tw.w << 1) | (tw.z >> 31);
-        const int base = tid * 128;
-#pragma unroll
-        for (int q = 0; q <= RC; q++) {  // (one more than a thread caches: its presence declines the tile)
-            int p = -1;
-            if (m0) { p = base + __ffs(m0) - 1; m0 &= m0 - 1; }
-            else if (m1) { p = base + 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
-            else if (m2) { p = base + 64 + __ffs(m2) - 1; m2 &= m2 - 1; }
-            else if (m3) { p = base + 96 + __ffs(m3) - 1; m3 &= m3 - 1; }
-            st[q] = p;
-        }
-        if (st[RC] >= 0) irregular = true;  // more lines start in this slice than a thread caches
-    }
-    // ---- per line (independent of one another: the loop is unrolled and the loads of different lines overlap)
-#pragma unroll
-    for (int q = 0; q < RC; q++) {
-#pragma unroll
-        for (int k = 0; k < K; k++) cf[q][k] = 0;
-        const int s = st[q];
-        if (s >= 0) {
-            // the line ends at the terminator before the next line's start; the last line of the slice searches for it
-            const int e_nl = st[q + 1] >= 0 ? st[q + 1] - 1 : ft_next_bit(sm.Tb, s);
-            if (e_nl >= WIN) irregular = true;  // runs past the window
-            else {
-                int e = e_nl;
-                if (e > s && sm.data[PRE + e - 1] == '\r') e--;
-                if (e > s) {  // a record (else: an empty line)
-                    int w = s >> 5;
-                    uint32_t m = sm.Sb[w] & (0xffffffffu << (s & 31));
-                    int fbeg = s, f = 0;
-                    bool eol = false;
-                    uint32_t present = 0, eq = 0;
-#pragma unroll
-                    for (int k = 0; k < K; k++) {
-                        if (!eol) {
-                            const int target = P.sel_field[k];
-                            while (f < target) {
-                                while (m == 0) m = sm.Sb[++w];
-                                const int p = (w << 5) + __ffs(m) - 1; m &= m - 1;
-                                if (p >= e_nl) { eol = true; break; }
-                                fbeg = p + 1; f++;
-                            }
-                            if (!eol) {
-                                while (m == 0) m = sm.Sb[++w];
-                                const int p = (w << 5) + __ffs(m) - 1; m &= m - 1;
-                                const bool last = p >= e_nl;
-                                const uint32_t len = (uint32_t)((last ? e : p) - fbeg);
-                                cf[q][k] = (uint32_t)fbeg | (len << 16);
-                                present |= 1u << k;
-                                uint32_t tm = HP ? P.slot_terms[k] : 0u;
-                                while (tm) {
-                                    const int t = __ffs(tm) - 1; tm &= tm - 1;
-                                    if (len == P.pred.term_len[t]) {
-                                        const bool same = lits_in_smem ? field_eq_smem(sm.data, PRE + fbeg, sm.lits, P.pred.term_off[t], len)
-                                                                       : bytes_eq(sm.data + PRE + fbeg, lits + P.pred.term_off[t], len);
-                                        if (same) eq |= 1u << t;
-                                    }
-                                }
-                                if (last) eol = true; else { fbeg = p + 1; f++; }
-                            }
-                        }
-                    }
-                    if (present != (1u << K) - 1u) irregular = true;  // a selected column is missing: error or padding
-                    if (P.expect_fields > 0) {
-                        int nf = f + 1;
-                        if (!eol) {
-                            const int we = e_nl >> 5;
-                            const uint32_t em = (1u << (e_nl & 31)) - 1u;
-                            if (w == we) nf += __popc(m & em);
-                            else {
-                                nf += __popc(m);
-                                for (int ww = w + 1; ww < we; ww++) nf += __popc(sm.Sb[ww]);
-                                nf += __popc(sm.Sb[we] & em);
-                            }
-                        }
-                        if (nf != P.expect_fields) irregular = true;  // wrong number of fields
-                    }
-                    if (!HP || eval_pred(P.pred, eq)) {
-                        if (nrow == 0) first_surv = nrec;
-                        nrow++;
-                        cmask |= 1u << q;
-#pragma unroll
-                        for (int k = 0; k < K; k++) cb[k] += cf[q][k] >> 16;
-                    }
-                    nrec++;
-                }
-            }
-        }
-    }
-    // ---- warp scans (16-bit fields: the totals of a tile are < 64 Ki)
-    uint32_t v[NW], inc[NW];
-    v[0] = nrec | (nrow << 16);
-#pragma unroll
-    for (int j = 1; j < NW; j++) {
-        v[j] = 0;
-#pragma unroll
-        for (int k = 0; k < K; k++) if (k / 2 == j - 1) v[j] |= cb[k] << (16 * (k & 1));
-    }
-#pragma unroll
-    for (int j = 0; j < NW; j++) {
-        inc[j] = warp_incl_scan(v[j]);
-        if (lane == 31) sm.wtot[j][warp] = inc[j];
-    }
-    {  // a warp stages one column of its rows at a time: it must fit its buffer
-        uint32_t big = 0;
-#pragma unroll
-        for (int j = 1; j < NW; j++) {
-            const uint32_t t = __shfl_sync(0xffffffffu, inc[j], 31);
-            if ((t & 0xffffu) > (uint32_t)FT_WSTAGE || (t >> 16) > (uint32_t)FT_WSTAGE) big = 1;
-        }
-        if (big) irregular = true;
-    }
-    // ---- the quote parity at the tile start must be 0 (verified against the chain, as general_tile does)
-    if (warp == 0) {
-        const uint32_t pv = lookback_parity_w0(P.st1, tile);
-        if (lane == 0) st_release_u32(&P.st1[tile], 2u | (pv << 2));
-        if (pv) irregular = true;
-    }
-    if (__syncthreads_or(irregular)) return false;
-
-    // ---- block scan
-    uint32_t ex[NW], tot[NW];
-#pragma unroll
-    for (int j = 0; j < NW; j++) {
-        ex[j] = inc[j] - v[j]; tot[j] = 0;
-#pragma unroll
-        for (int i = 0; i < THREADS / 32; i++) { const uint32_t t = sm.wtot[j][i]; if (i < warp) ex[j] += t; tot[j] += t; }
-    }
-    // ---- chain 2: global prefix of (records, rows, bytes[k])
-    constexpr int NP = 2 + K;
-    {
-        unsigned long long mine = 0;  // component `tid` of this tile's totals
-        if (tid == 0) mine = tot[0] & 0xffffu;
-        else if (tid == 1) mine = tot[0] >> 16;
-#pragma unroll
-        for (int k = 0; k < K; k++) if (tid == 2 + k) mine = (tot[1 + k / 2] >> (16 * (k & 1))) & 0xffffu;
-        unsigned long long* wt = P.words + (uint64_t)tile * NP;
-        if (tid < NP) st_relaxed_u64((uint64_t*)(wt + tid), LB_AGG | mine);
-        if (warp == 0) {
-            lookback_totals_w0<K>(P.words, tile, NP, sm);
-            if (lane < NP) st_relaxed_u64((uint64_t*)(wt + lane), LB_INCL | (sm.tile_prefix[lane] + mine));
-        }
-        __syncthreads();
-    }
-    const uint64_t rec0 = sm.tile_prefix[0] + (ex[0] & 0xffffu);
-    const uint64_t row0 = sm.tile_prefix[1] + (ex[0] >> 16);  // global row of my first surviving row
-    if (nrow != 0 && row0 == 0) P.result->first_row_ordinal = rec0 + first_surv;
-    // the whole tile must fit the output buffers (else nothing of it is written: the host reruns with exact sizes)
-    bool fits = sm.tile_prefix[1] + (tot[0] >> 16) <= P.row_cap;
-#pragma unroll
-    for (int k = 0; k < K; k++) fits = fits && sm.tile_prefix[2 + k] + ((tot[1 + k / 2] >> (16 * (k & 1))) & 0xffffu) <= P.data_cap[k];
-    if (!fits) return true;
-
-    // ---- output, warp by warp (the buffers overlay the bitmaps: every warp is past pass 1, see the vote above)
-    FastWarpBuf& wb = reinterpret_cast<FastWarpBuf*>(sm.Tb)[warp];
-    const uint32_t wrows = __shfl_sync(0xffffffffu, inc[0], 31) >> 16;          // rows of this warp
-    const uint64_t wrow0 = __shfl_sync(0xffffffffu, row0, 0);                   // global row of its first row
-    const uint32_t lrow = (uint32_t)(row0 - wrow0);                             // my first row inside the warp
-    if (wrows == 0) return true;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const uint32_t exk = (ex[1 + k / 2] >> (16 * (k & 1))) & 0xffffu;
-        const uint32_t wbytes = (__shfl_sync(0xffffffffu, inc[1 + k / 2], 31) >> (16 * (k & 1))) & 0xffffu;
-        const uint64_t g0 = sm.tile_prefix[2 + k] + exk;                         // global byte offset of my first value
-        const uint64_t wg0 = __shfl_sync(0xffffffffu, g0, 0);                   // ... of the warp's first value
-        const uint32_t sh = (uint32_t)(wg0 & 15);
-        // offsets and bytes of my rows
-        {
-            uint32_t j = lrow, run = (uint32_t)(g0 - wg0);
-#pragma unroll
-            for (int q = 0; q < RC; q++) {
-                if ((cmask >> q) & 1) {
-                    const uint32_t f = cf[q][k], len = f >> 16;
-                    wb.off[j++] = (uint32_t)wg0 + run;
-                    const uint8_t* sp = sm.data + PRE + (f & 0xffffu);
-                    uint8_t* dp = wb.stage + sh + run;
-                    for (uint32_t x = 0; x < len; x++) dp[x] = sp[x];
-                    run += len;
-                }
-            }
-        }
-        __syncwarp();
-        for (uint32_t i = lane; i < wrows; i += 32) P.out_off[k][wrow0 + i] = wb.off[i];
-        {
-            uint8_t* gb = P.out_data[k] + (wg0 - sh);  // 16-byte aligned
-            const uint32_t end = sh + wbytes;
-            for (uint32_t x = lane * 16; x < end; x += 32 * 16) {
-                if (x >= sh && x + 16 <= end) *reinterpret_cast<uint4*>(gb + x) = *reinterpret_cast<const uint4*>(wb.stage + x);
-                else for (uint32_t y = x > sh ? x : sh; y < x + 16 && y < end; y++) gb[y] = wb.stage[y];
-            }
-        }
-        __syncwarp();
-    }
-    return true;
+    return m_last_v;
 }
 
 template <int KMAX, bool EXACT, bool HP>
 __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_scan_kernel(const __grid_constant__ ParseParams P) {
-    constexpr bool FAST_OK = EXACT && KMAX <= 8;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ParseSmem& sm = *reinterpret_cast<ParseSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1304,14 +658,422 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
         }
         if (tid < 4) { sm.Tb[WIN_WORDS + tid] = 0; sm.Sb[WIN_WORDS + tid] = 0; sm.Qb[WIN_WORDS + tid] = 0; }
         const bool hasq = __syncthreads_or(anyq != 0);
-        // chain 1: a tile without quotes leaves the parity as it finds it — published at once (general_tile repeats it)
-        if (!hasq && tid == 0) st_release_u32(&P.st1[tile], tile == 0 ? (2u | (P.pin0 << 2)) : 1u);
-        bool done = false;
-        if (FAST_OK && !P.no_fast && !hasq && tile != 0 && !eof_in_win && rel_ds <= 0 && tile_base + TILE <= P.own_end)
-            done = fast_tile<KMAX, HP>(P, sm, tile, tile_base, lits, lits_in_smem);
-        if (!done) {
-            if (tid == 0) atomicAdd(&P.result->general_tiles, 1u);
-            general_tile<KMAX, EXACT, HP>(P, sm, tile, tile_base, rel_n64, hasq, lits, lits_in_smem);
+        uint32_t tile_par = 0;
+        if (hasq) {
+            uint16_t* Q16 = reinterpret_cast<uint16_t*>(sm.Qb);
+            for (int v = tid; v < WIN / 16; v += THREADS) {
+                uint4 x = d4[v];
+                Q16[v] = (uint16_t)flags16(eq_flags(x.x, Q4), eq_flags(x.y, Q4), eq_flags(x.z, Q4), eq_flags(x.w, Q4));
+            }
+            __syncthreads();
+            uint32_t par = 0;
+            for (int w = tid; w < TILE_WORDS; w += THREADS) par ^= __popc(sm.Qb[w]);
+            tile_par = __syncthreads_count(par & 1) & 1;
+        }
+        // ---- chain 1: quote parity at the tile start.  The tile's own parity is published at once; a tile
+        // without quotes does not wait for its predecessors here: it proceeds assuming it starts outside
+        // quotes and verifies that after pass 1 (the rare miss redoes the tile from `retry`).
+        if (tid == 0) st_release_u32(&P.st1[tile], tile == 0 ? (2u | ((P.pin0 ^ tile_par) << 2)) : (1u | (tile_par << 2)));
+        uint32_t pin = tile == 0 ? P.pin0 : 0;
+        bool pin_known = tile == 0;
+        if (hasq && !pin_known) {
+            if (warp == 0) {
+                const uint32_t pv = lookback_parity_w0(P.st1, tile);
+                if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
+            }
+            __syncthreads();
+            pin = sm.pin;
+            pin_known = true;
+        }
+    retry:
+        if (hasq || pin) {
+            // in-quote mask by prefix-XOR of the quote bitmap; terminators are newlines outside quotes
+            uint32_t carry = pin;
+            for (int r0 = 0; r0 < WIN_WORDS; r0 += THREADS) {
+                int w = r0 + tid;
+                uint32_t q = (w < WIN_WORDS && hasq) ? sm.Qb[w] : 0;
+                uint32_t px = q; px ^= px << 1; px ^= px << 2; px ^= px << 4; px ^= px << 8; px ^= px << 16;
+                uint32_t bal = __ballot_sync(0xffffffffu, px >> 31);
+                uint32_t before = __popc(bal & lanemask_lt()) & 1;
+                if (lane == 0) sm.wpar[warp] = __popc(bal) & 1;
+                __syncthreads();
+                uint32_t c = carry, tot = 0;
+                for (int i = 0; i < THREADS / 32; i++) { if (i < warp) c ^= sm.wpar[i]; tot ^= sm.wpar[i]; }
+                uint32_t cin = c ^ before;
+                uint32_t iq = (px ^ q) ^ (0u - cin);
+                if (w < WIN_WORDS) sm.Tb[w] &= ~iq;  // (Sb keeps quoted newlines/delimiters: only lines with quotes see them)
+                carry ^= tot;
+                __syncthreads();
+            }
+        }
+        // a virtual terminator at EOF closes a last line that has no newline
+        if (eof_in_win && tid == 0) { sm.Tb[rel_n >> 5] |= 1u << (rel_n & 31); sm.Sb[rel_n >> 5] |= 1u << (rel_n & 31); }
+        if (eof_in_win) __syncthreads();
+
+        // ---- flat structural index
+        uint4 tw = reinterpret_cast<const uint4*>(sm.Tb)[tid];
+        {
+            const uint4 sw = reinterpret_cast<const uint4*>(sm.Sb)[tid];
+            const uint32_t tws[4] = {tw.x, tw.y, tw.z, tw.w}, sws[4] = {sw.x, sw.y, sw.z, sw.w};
+            uint32_t cs = __popc(sw.x) + __popc(sw.y) + __popc(sw.z) + __popc(sw.w);
+            uint32_t ct = __popc(tw.x) + __popc(tw.y) + __popc(tw.z) + __popc(tw.w);
+            uint32_t v = cs | (ct << 16);
+            uint32_t inc = warp_incl_scan(v);
+            if (lane == 31) sm.wtot[0][warp] = inc;
+            // the 64 halo words: one per thread of warps 0-1
+            uint32_t hs = 0, ht = 0, hv = 0, hinc = 0;
+            if (tid < HALO_WORDS) { hs = sm.Sb[TILE_WORDS + tid]; ht = sm.Tb[TILE_WORDS + tid]; hv = __popc(hs) | (__popc(ht) << 16); }
+            if (warp < HALO_WORDS / 32) { hinc = warp_incl_scan(hv); if (lane == 31) sm.wtot[1][warp] = hinc; }
+            __syncthreads();
+            uint32_t ex = inc - v, tile_tot = 0;
+#pragma unroll
+            for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) ex += t; tile_tot += t; }
+            uint32_t o = ex & 0xffffu, tc = ex >> 16;
+            uint32_t halo_tot = 0;
+            for (int i = 0; i < HALO_WORDS / 32; i++) halo_tot += sm.wtot[1][i];
+            // the totals are known before the expansion: a window that does not fit skips it (dense fallback), one
+            // that fits needs no bounds checks
+            const bool fits = (tile_tot & 0xffffu) + (halo_tot & 0xffffu) <= (uint32_t)SCAP && (tile_tot >> 16) + (halo_tot >> 16) <= (uint32_t)LCAP;
+            if (fits) {
+#pragma unroll
+                for (int j = 0; j < WPT; j++) {
+                    uint32_t m = sws[j];
+                    const int pos0 = (tid * WPT + j) * 32;
+                    uint32_t tm = tws[j];
+                    while (tm) {  // terminators are ~7x sparser than structurals: their ordinals come from a popcount
+                        int bpos = __ffs(tm) - 1; tm &= tm - 1;
+                        sm.ord[tc++] = (uint16_t)(o + __popc(m & ((1u << bpos) - 1)));
+                    }
+                    while (m) {
+                        int bpos = __ffs(m) - 1; m &= m - 1;
+                        sm.sidx[o++] = (uint16_t)(pos0 + bpos);
+                    }
+                }
+            }
+            if (fits && tid < HALO_WORDS) {
+                uint32_t hex = hinc - hv;
+                for (int i = 0; i < warp; i++) hex += sm.wtot[1][i];
+                uint32_t o2 = (tile_tot & 0xffffu) + (hex & 0xffffu), tc2 = (tile_tot >> 16) + (hex >> 16);
+                uint32_t m = hs;
+                const int pos0 = (TILE_WORDS + tid) * 32;
+                while (m) {
+                    int bpos = __ffs(m) - 1; m &= m - 1;
+                    sm.sidx[o2] = (uint16_t)(pos0 + bpos);
+                    if ((ht >> bpos) & 1) sm.ord[tc2++] = (uint16_t)o2;
+                    o2++;
+                }
+            }
+            if (tid == 0) { sm.nstruct = (tile_tot & 0xffffu) + (halo_tot & 0xffffu); sm.nterm = (tile_tot >> 16) + (halo_tot >> 16); }
+            // terminators of the tile proper (tile_tot >> 16) are needed below: stash in wpar[0]
+            if (tid == 0) sm.wpar[0] = tile_tot >> 16;
+            __syncthreads();
+        }
+        const int nterm = (int)sm.nterm;
+        const bool flat_ok = sm.nstruct <= SCAP && sm.nterm <= LCAP;
+        const bool first_owned = tile_base == 0 || (sm.data[PRE - 1] == '\n' && pin == 0);
+        // lines 1..m start inside the tile proper (terminator i-1 at position <= TILE-2); line 0 iff first_owned
+        const int m_last = (int)sm.wpar[0] - (int)((sm.Tb[TILE_WORDS - 1] >> 31) & 1);
+        const int i0 = first_owned ? 0 : 1;
+        int m_last_v = m_last;
+        if (P.own_end != ~0ull && flat_ok)  // a byte-range shard that is not the file's last (uniform, cold, out of line)
+            m_last_v = shard_tile_tail(P, sm, tile, tile_base, i0, m_last, nterm, rel_n, rel_ds);
+        const int nown = m_last_v - i0 + 1;
+        const int L = (nown + THREADS - 1) / THREADS;
+        ByteSrc src{P.in, P.n, sm.data + PRE, tile_base, tile_base + (uint64_t)rel_n};
+
+        // record-start bits of this thread's 4 words (dense fallback only)
+        uint32_t rs[WPT] = {0, 0, 0, 0};
+        if (!flat_ok) {
+            uint32_t prev = tid == 0 ? (first_owned && tile_base > 0 ? 0x80000000u : 0u) : sm.Tb[tid * WPT - 1];
+            rs[0] = (tw.x << 1) | (prev >> 31);
+            rs[1] = (tw.y << 1) | (tw.x >> 31);
+            rs[2] = (tw.z << 1) | (tw.y >> 31);
+            rs[3] = (tw.w << 1) | (tw.z >> 31);
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                const int64_t b0 = (int64_t)(tid * WPT + j) * 32;
+                uint32_t keep = 0xffffffffu;
+                if (rel_ds > b0) keep = rel_ds >= b0 + 32 ? 0u : (0xffffffffu << (rel_ds - b0));
+                if (rel_n64 < b0 + 32) keep &= rel_n64 <= b0 ? 0u : (0xffffffffu >> (32 - (rel_n64 - b0)));
+                rs[j] &= keep;
+                if (P.ds_is_start && rel_ds >= b0 && rel_ds < b0 + 32 && rel_ds < rel_n64) rs[j] |= 1u << (rel_ds - b0);
+            }
+            if (tid == 0 && tile_base == 0 && rel_ds <= 0) rs[0] |= 1u;  // file start
+            if (tid == 0) atomicAdd(&P.result->fallback_tiles, 1u);
+        }
+
+        // ---- pass 1: count records / surviving rows / bytes per column
+        uint32_t nrec = 0, nrow = 0, cb[KMAX];
+        uint32_t my_err = 0xffffffffu;  // (local record idx << 16) | kind << 8 | slot
+        uint32_t err_rows_local = 0, first_surv_rec = 0;
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) cb[k] = 0;
+        auto account = [&](const Rec<KMAX>& r) -> bool {
+            bool survived = false;
+            if (r.err != K_OK) {
+                if (my_err == 0xffffffffu) { my_err = (nrec << 16) | ((uint32_t)r.err << 8) | (uint32_t)r.err_slot; err_rows_local = nrow; }
+            } else if (!HP || eval_pred(P.pred, r.eq)) {
+                if (nrow == 0) first_surv_rec = nrec;
+                nrow++;
+                survived = true;
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) cb[k] += r.slow ? r.f[k] : (r.f[k] >> 16);
+            }
+            nrec++;
+            return survived;
+        };
+        // pass-1 results of the first RC lines of a thread stay in registers so that pass 2 only writes
+        constexpr int RC = KMAX <= 4 ? 6 : (KMAX <= 8 ? 3 : 1);
+        uint32_t cf[RC][KMAX];
+        uint32_t cmask = 0;
+        bool any_slow = false;
+        if (flat_ok) {
+#pragma unroll
+            for (int q = 0; q < RC; q++) {
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) cf[q][k] = 0;
+                const int i = i0 + tid * L + q;
+                if (q < L && i <= m_last_v) {
+                    Rec<KMAX> r;
+                    if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
+                        const bool surv = account(r);
+                        if (r.slow) any_slow = true;
+                        else if (surv) {
+                            cmask |= 1u << q;
+#pragma unroll
+                            for (int k = 0; k < KMAX; k++) cf[q][k] = r.f[k];
+                        }
+                    }
+                }
+            }
+            for (int q = RC; q < L; q++) {
+                const int i = i0 + tid * L + q;
+                if (i > m_last_v) break;
+                Rec<KMAX> r;
+                if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < WPT; j++) {
+                uint32_t m = rs[j];
+                while (m) {
+                    int b = __ffs(m) - 1; m &= m - 1;
+                    Rec<KMAX> r;
+                    if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, (tid * WPT + j) * 32 + b, rel_n, r)) account(r);
+                }
+            }
+        }
+        if (!pin_known) {  // verify the optimistic assumption "this tile starts outside quotes"
+            if (warp == 0) {
+                const uint32_t pv = lookback_parity_w0(P.st1, tile);
+                if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
+            }
+            __syncthreads();
+            pin = sm.pin;
+            pin_known = true;
+            if (pin) goto retry;
+        }
+        // staged output (coalesced stores) needs every row of the tile cached and on the fast path
+        const bool staged_pre = !__syncthreads_or(any_slow) && flat_ok && L <= RC;
+        // ---- block scan of (records | rows << 16, bytes[k])
+        uint32_t v0 = nrec | (nrow << 16);
+        uint32_t i0s = warp_incl_scan(v0);
+        uint32_t ik[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) ik[k] = warp_incl_scan(cb[k]);
+        if (lane == 31) {
+            sm.wtot[0][warp] = i0s;
+#pragma unroll
+            for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) sm.wtot[1 + k][warp] = ik[k];
+        }
+        __syncthreads();
+        uint32_t ex0 = i0s - v0, tot0 = 0;
+        uint32_t exk[KMAX], totk[KMAX];
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) ex0 += t; tot0 += t; }
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+            exk[k] = 0; totk[k] = 0;
+            if (k < (EXACT ? KMAX : P.nsel)) {
+                exk[k] = ik[k] - cb[k];
+#pragma unroll
+                for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[1 + k][i]; if (i < warp) exk[k] += t; totk[k] += t; }
+            }
+        }
+        const bool staged = staged_pre && (tot0 >> 16) <= (uint32_t)LCAP;
+        // ---- chain 2: global prefix of (records, rows, bytes[k])
+        {
+            unsigned long long mine = 0;  // component `tid` of this tile's totals
+            if (tid == 0) mine = tot0 & 0xffffu;
+            else if (tid == 1) mine = tot0 >> 16;
+#pragma unroll
+            for (int k = 0; k < KMAX; k++) if (tid == 2 + k) mine = totk[k];
+            unsigned long long* wt = P.words + (uint64_t)tile * NP;
+            if (tile == 0) {
+                if (tid < NP) { st_relaxed_u64((uint64_t*)(wt + tid), LB_INCL | mine); sm.tile_prefix[tid] = 0; }
+                __syncthreads();
+            } else {
+                if (tid < NP) st_relaxed_u64((uint64_t*)(wt + tid), LB_AGG | mine);
+                if (warp == 0) {
+                    lookback_totals_w0<KMAX>(P.words, tile, NP, sm);
+                    if (lane < NP) st_relaxed_u64((uint64_t*)(wt + lane), LB_INCL | (sm.tile_prefix[lane] + mine));
+                }
+                __syncthreads();
+            }
+            if (tile == P.ntiles - 1 && tid < NP) {  // totals + end-of-column sentinels
+                const unsigned long long total = sm.tile_prefix[tid] + mine;
+                P.result->totals[tid] = total;
+                sm.col_total[tid] = total;
+            }
+            if (tile == P.ntiles - 1) {
+                __syncthreads();
+                const unsigned long long rows = sm.col_total[1];
+                if (tid >= 2 && tid < NP && rows <= P.row_cap) P.out_off[tid - 2][rows] = (uint32_t)sm.col_total[tid];
+            }
+        }
+
+        // ---- pass 2: write offsets, gather field bytes
+        {
+            const uint64_t rec0 = sm.tile_prefix[0] + (ex0 & 0xffffu);
+            uint64_t row = sm.tile_prefix[1] + (ex0 >> 16);
+            if (my_err != 0xffffffffu) {
+                unsigned long long key = ((rec0 + (my_err >> 16)) << 16) | (my_err & 0xffffu);
+                atomicMin(&P.result->err_key, key);
+                atomicMin(&P.result->err_rows, (unsigned long long)(row + err_rows_local));
+            }
+            if (staged) {
+                // Tb|Sb|Qb|sidx|ord are dead once pass 1 has cached every row: their 33 KB hold, per column, the
+                // row list (source extent, destination offset) and a staging buffer, so that rows are copied by
+                // all threads evenly and HBM sees full, aligned 16-byte stores.
+                uint32_t* ost = reinterpret_cast<uint32_t*>(sm.Tb);  // [LCAP + 4] destination offsets of the tile's rows
+                uint32_t* wl = ost + (LCAP + 4);                      // [LCAP]     beg | len << 16 of the field
+                uint8_t* stage = reinterpret_cast<uint8_t*>(wl + LCAP);
+                constexpr uint32_t REGION = 3 * (WIN_WORDS + 4) * 4 + SCAP * 2 + LCAP * 2;
+                constexpr uint32_t CH = ((REGION - (2 * LCAP + 4) * 4) / 16) * 16;
+                const uint32_t tile_rows = tot0 >> 16;
+                const uint64_t row_base = sm.tile_prefix[1];
+                const uint32_t osh = (uint32_t)(row_base & 3);
+                if (nrow != 0 && row == 0) P.result->first_row_ordinal = rec0 + first_surv_rec;
+                // (a run-time column loop -- one copy of the staging code instead of KMAX -- measured slower: 679 vs 736 GB/s)
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) {
+                    if (k < (EXACT ? KMAX : P.nsel)) {
+                        const uint64_t dbase = sm.tile_prefix[2 + k];
+                        uint32_t myf[RC], exk_k = 0, totk_k = 0;
+#pragma unroll
+                        for (int kk = 0; kk < KMAX; kk++) if (kk == k) { exk_k = exk[kk]; totk_k = totk[kk]; }
+#pragma unroll
+                        for (int q = 0; q < RC; q++) {
+                            myf[q] = 0;
+#pragma unroll
+                            for (int kk = 0; kk < KMAX; kk++) if (kk == k) myf[q] = cf[q][kk];
+                        }
+                        {
+                            uint32_t j = ex0 >> 16, run = exk_k;
+#pragma unroll
+                            for (int q = 0; q < RC; q++)
+                                if ((cmask >> q) & 1) { ost[osh + j] = (uint32_t)(dbase + run); wl[j] = myf[q]; j++; run += myf[q] >> 16; }
+                        }
+                        __syncthreads();
+                        // ---- offsets of this tile's rows
+                        {
+                            uint32_t* gout = P.out_off[k] + (row_base - osh);
+                            const uint64_t rows_ok = P.row_cap > row_base ? P.row_cap - row_base : 0;  // rows of this tile that fit
+                            const uint32_t lim_e = osh + (uint32_t)(tile_rows < rows_ok ? tile_rows : rows_ok);
+                            for (uint32_t e = tid * 4; e < lim_e; e += THREADS * 4)
+                                if (e >= osh && e + 4 <= lim_e) *reinterpret_cast<uint4*>(gout + e) = *reinterpret_cast<const uint4*>(ost + e);
+                            if (tid < 8) {  // partial first / last vector: one element per lane
+                                const uint32_t tv0 = lim_e & ~3u;
+                                const uint32_t x = tid < 4 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 4);
+                                const bool head = tid < 4 && osh != 0;
+                                const bool tail = tid >= 4 && (lim_e & 3u) != 0 && !(tv0 == 0 && osh != 0);
+                                if ((head || tail) && x >= osh && x < lim_e) gout[x] = ost[x];
+                            }
+                        }
+                        // ---- field bytes
+                        const uint32_t B = totk_k;
+                        const uint32_t r16 = (uint32_t)(dbase & 15);
+                        const uint64_t room = P.data_cap[k] > dbase ? P.data_cap[k] - dbase : 0;
+                        const uint32_t hi_ok = r16 + (uint32_t)(B < room ? B : room);  // shifted local end of writable bytes
+                        uint8_t* gbase = P.out_data[k] + (dbase - r16);
+                        for (uint32_t c0 = 0; c0 < r16 + B; c0 += CH) {
+                            for (uint32_t j = tid; j < tile_rows; j += THREADS) {
+                                const uint32_t f = wl[j], len = f >> 16;
+                                const uint32_t st = ost[osh + j] - (uint32_t)dbase + r16;  // shifted tile-local start
+                                const uint32_t lo = st > c0 ? st : c0, hi = st + len < c0 + CH ? st + len : c0 + CH;
+                                const uint8_t* sp = sm.data + PRE + (f & 0xffffu) - st;
+                                for (uint32_t x = lo; x < hi; x++) stage[x - c0] = sp[x];  // (word-wise copies measured slower)
+                            }
+                            __syncthreads();
+                            const uint32_t cend = c0 + CH < r16 + B ? c0 + CH : r16 + B;
+                            for (uint32_t x0 = c0 + tid * 16; x0 < cend; x0 += THREADS * 16)
+                                if (x0 >= r16 && x0 + 16 <= hi_ok) *reinterpret_cast<uint4*>(gbase + x0) = *reinterpret_cast<const uint4*>(stage + (x0 - c0));
+                            // the (at most two) partial vectors at the column's first and last byte: one byte per lane
+                            if (tid < 32) {
+                                const uint32_t tv0 = hi_ok & ~15u;
+                                const uint32_t x = tid < 16 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 16);
+                                const bool head = tid < 16 && c0 == 0 && r16 != 0;
+                                const bool tail = tid >= 16 && (hi_ok & 15u) != 0 && tv0 >= c0 && tv0 < cend && !(tv0 == 0 && r16 != 0);
+                                if ((head || tail) && x >= r16 && x < hi_ok) gbase[x] = stage[x - c0];
+                            }
+                            __syncthreads();
+                        }
+                        __syncthreads();
+                    }
+                }
+            } else if (nrow != 0) {
+                uint64_t off[KMAX];
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) off[k] = k < (EXACT ? KMAX : P.nsel) ? sm.tile_prefix[2 + k] + exk[k] : 0;
+                uint32_t rec_local = 0;
+                auto emit = [&](const Rec<KMAX>& r, uint64_t start_abs) {
+                    if (r.err != K_OK || (HP && !eval_pred(P.pred, r.eq))) { rec_local++; return; }
+                    if (row == 0) P.result->first_row_ordinal = rec0 + rec_local;
+                    const bool row_ok = row < P.row_cap;
+                    if (r.slow) {
+                        uint64_t dst_off[MAXSEL];
+                        uint32_t maxlen[MAXSEL];
+                        SlowOut so;
+#pragma unroll
+                        for (int k = 0; k < KMAX; k++) { dst_off[k] = off[k]; maxlen[k] = r.f[k]; }
+                        slow_record(P, src, start_abs, true, dst_off, maxlen, &so);
+                    }
+#pragma unroll
+                    for (int k = 0; k < KMAX; k++) {
+                        if (k < (EXACT ? KMAX : P.nsel)) {
+                            uint32_t len = r.slow ? r.f[k] : (r.f[k] >> 16);
+                            if (row_ok) P.out_off[k][row] = (uint32_t)off[k];
+                            if (!r.slow && off[k] + len <= P.data_cap[k]) {
+                                const uint8_t* s = sm.data + PRE + (r.f[k] & 0xffffu);
+                                uint8_t* d = P.out_data[k] + off[k];
+                                for (uint32_t i = 0; i < len; i++) d[i] = s[i];
+                            }
+                            off[k] += len;
+                        }
+                    }
+                    row++; rec_local++;
+                };
+                if (flat_ok) {
+                    for (int q = 0; q < L; q++) {
+                        const int i = i0 + tid * L + q;
+                        if (i > m_last_v) break;
+                        Rec<KMAX> r;
+                        if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
+                            emit(r, tile_base + (i == 0 ? 0 : (uint64_t)sm.sidx[sm.ord[i - 1]] + 1));
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < WPT; j++) {
+                        uint32_t m = rs[j];
+                        while (m) {
+                            int b = __ffs(m) - 1; m &= m - 1;
+                            const int ws = (tid * WPT + j) * 32 + b;
+                            Rec<KMAX> r;
+                            if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, ws, rel_n, r)) emit(r, tile_base + ws);
+                        }
+                    }
+                }
+            }
         }
         __syncthreads();  // smem is reused by the next tile
     }

@@ -166,6 +166,9 @@ int cpb_table_select(cpb_ctx* ctx, const cpb_table* t, const cpb_str* cols, int 
 int cpb_table_drop(cpb_ctx* ctx, const cpb_table* t, const cpb_str* cols, int n, cpb_table** out);
 /* DataSource.Filter with Like/All/Any/Not (csvplus.go:276-286, :1243-1293) */
 int cpb_table_filter(cpb_ctx* ctx, const cpb_table* t, const cpb_pred* pred, cpb_table** out);
+/* DataSource.TakeWhile / DropWhile (csvplus.go:346-374) with a recognisable predicate: the first row for which it is
+ * false (the row count when there is none); TakeWhile = cpb_table_slice(0, row), DropWhile = cpb_table_slice(row, n) */
+int cpb_table_first_false(cpb_ctx* ctx, const cpb_table* t, const cpb_pred* pred, int64_t* row);
 /* Top(n)/Drop(n) as row-range views (csvplus.go:313-342) */
 int cpb_table_slice(cpb_ctx* ctx, const cpb_table* t, int64_t row_lo, int64_t row_hi, cpb_table** out);
 void cpb_table_free(cpb_table* t);

@@ -684,6 +684,36 @@ orc_result* orc_select(const orc_result* src, int n, const char* names, const in
     return r;
 }
 
+// DataSource.Top / Drop / TakeWhile / DropWhile, csvplus.go:313-374, and DropColumns :493-507.  A source that stops early
+// (Top, TakeWhile return io.EOF) never reaches an error further down the input.
+// mode 0 Top(n), 1 Drop(n), 2 TakeWhile(pred), 3 DropWhile(pred)
+orc_result* orc_cut(const orc_result* src, int mode, uint64_t n, const orc_pred* pred) {
+    auto* r = new Result();
+    bool stopped = false, yield = false;
+    uint64_t counter = n;
+    for (auto& row : src->rows) {
+        if (mode == 0) { if (counter == 0) { stopped = true; break; } counter--; r->rows.push_back(row); }
+        else if (mode == 1) { if (counter == 0) r->rows.push_back(row); else counter--; }
+        else if (mode == 2) { if (!pred->eval(row)) { stopped = true; break; } r->rows.push_back(row); }
+        else { if ((yield = yield || !pred->eval(row))) r->rows.push_back(row); }
+    }
+    // Top(n) asks for one more row before it stops (csvplus.go:317-323): with exactly n rows delivered before an error
+    // of the source the error still surfaces; TakeWhile stops on the first failing row it SEES
+    if (!stopped) { r->failed = src->failed; r->line = src->line; r->msg = src->msg; r->kind = src->kind; }
+    return r;
+}
+orc_result* orc_drop_columns(const orc_result* src, int n, const char* names, const int64_t* name_lens) {
+    auto cols = unpack_list(names, name_lens, n);
+    auto* r = new Result();
+    for (auto& row : src->rows) {
+        Row out = row;
+        for (auto& c : cols) out.erase(c);
+        r->rows.push_back(std::move(out));
+    }
+    r->failed = src->failed; r->line = src->line; r->msg = src->msg; r->kind = src->kind;
+    return r;
+}
+
 // ---- index
 // IndexOn / UniqueIndexOn, csvplus.go:527-537.  err text (if any) copied to errbuf; returns NULL on error.
 orc_index* orc_index_create(const orc_result* src, int n, const char* names, const int64_t* name_lens, int unique, int stable,

@@ -62,6 +62,8 @@ def lib():
         L.orc_pred_free.argtypes = [vp]
         L.orc_filter.restype = vp; L.orc_filter.argtypes = [vp, vp]
         L.orc_select.restype = vp; L.orc_select.argtypes = [vp, C.c_int, cp, P(i64), u64]
+        L.orc_cut.restype = vp; L.orc_cut.argtypes = [vp, C.c_int, u64, vp]
+        L.orc_drop_columns.restype = vp; L.orc_drop_columns.argtypes = [vp, C.c_int, cp, P(i64)]
         L.orc_index_create.restype = vp
         L.orc_index_create.argtypes = [vp, C.c_int, cp, P(i64), C.c_int, C.c_int, vp, u64]
         L.orc_index_free.argtypes = [vp]
@@ -212,6 +214,14 @@ class Rows:
 
     def select(self, *cols, line_base=0):
         b, l, n = _pack(cols); return Rows(lib().orc_select(self.h, n, b, l, line_base))
+
+    def top(self, n): return Rows(lib().orc_cut(self.h, 0, n, None))
+    def drop(self, n): return Rows(lib().orc_cut(self.h, 1, n, None))
+    def take_while(self, pred: Pred): return Rows(lib().orc_cut(self.h, 2, 0, pred.h))
+    def drop_while(self, pred: Pred): return Rows(lib().orc_cut(self.h, 3, 0, pred.h))
+
+    def drop_columns(self, *cols):
+        b, l, n = _pack(cols); return Rows(lib().orc_drop_columns(self.h, n, b, l))
 
     def index_on(self, *cols, unique=False, stable=True):
         b, l, n = _pack(cols); eb = C.create_string_buffer(8192)

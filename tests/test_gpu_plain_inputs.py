@@ -1,7 +1,7 @@
-"""The lean tile path of csv_scan (parse_kernels.cuh: fast_tile) against the oracle: inputs without quotes spanning many
-32 KiB tiles so that interior tiles take the lean path, mixed with everything that must make a tile fall back to the
-general path mid-file (ragged lines, dense short lines, very long fields, a quote, an error) — the two paths share the
-look-back chains, so totals, offsets and error ordinals must stay exact across any mixture."""
+"""Quote-free inputs spanning many 32 KiB tiles of csv_scan against the oracle, mixed with what makes single tiles take the
+rare paths mid-file (ragged lines, dense short lines that overflow the flat index, fields longer than the look-ahead, one
+quote, one error): all tiles share the two look-back chains, so totals, offsets and error ordinals must stay exact across
+any mixture.  (Written while a separate lean path for regular tiles was tried — DESIGN.md §7; kept as parity cases.)"""
 import os
 import random
 
@@ -41,8 +41,8 @@ def _plain_csv(seed, nrows, ncols=6, crlf_p=0.0, blank_p=0.0, short_p=0.0, long_
     (1, dict()),
     (2, dict(crlf_p=1.0)),
     (3, dict(crlf_p=0.5, blank_p=0.2)),
-    (4, dict(short_p=0.9, width=(0, 3))),          # dense lines: more lines per 128-byte slice than a thread caches
-    (5, dict(long_p=0.01)),                         # fields longer than a warp's staging buffer / the 2 KiB halo
+    (4, dict(short_p=0.9, width=(0, 3))),          # dense lines: tiles whose structurals overflow the flat index
+    (5, dict(long_p=0.01)),                         # fields longer than the 2 KiB look-ahead
     (6, dict(eol_last=False)),
     (7, dict(ncols=3, width=(0, 6))),
     (8, dict(ncols=12, width=(1, 5))),
@@ -62,8 +62,8 @@ def test_plain_inputs_many_tiles(seed, kw):
 
 
 def test_irregular_lines_in_the_middle():
-    """one ragged line / one quoted field / one bare quote deep inside a regular file: the tile holding it takes the
-    general path, its neighbours the lean one; rows, offsets and the error ordinal stay exact"""
+    """one ragged line / one quoted field / one bare quote deep inside a regular file: rows, offsets and the error
+    ordinal stay exact"""
     base = _plain_csv(11, 30_000).split(b"\n")
     for patch, expect_err in (
         (b"a,b,c", "wrong number of fields"),
@@ -83,15 +83,15 @@ def test_irregular_lines_in_the_middle():
 
 
 def test_any_field_count_pads_short_lines():
-    """NumFieldsAny: short lines are padded with empty values — not a plain record, so its tile falls back"""
+    """NumFieldsAny: short lines are padded with empty values"""
     lines = _plain_csv(12, 20_000).split(b"\n")
     lines[9_000] = b"only,two"
     data = b"\n".join(lines)
     check_parity(data, opts=orc.Opts(fields_per_record=-1), select=["c0", "c1", "c4"])
 
 
-def test_lean_and_general_paths_agree_on_the_bench_shapes():
-    """people / orders / products of the synthetic generator, lean path vs general path (CPB_NO_FAST_TILE) vs oracle"""
+def test_bench_shapes_vs_oracle():
+    """people / orders / products of the synthetic generator vs the oracle"""
     import csvplus_b200 as cp
     ctx = gpu_ctx()
     for kind, spec, kw in (("people", ["name", "surname", "id"], {}), ("orders", ["cust_id", "prod_id", "qty", "ts"], dict(n_cust=1000, n_prod=50)),
