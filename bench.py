@@ -327,6 +327,9 @@ def main():
     import csvplus_b200 as cp
     torch.cuda.set_device(local)
     numa_node = bind_to_gpu_numa_node(local)
+    # (NCCL prints its version banner on stdout when the first communicator comes up: stdout carries the JSON line only)
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -344,6 +347,7 @@ def main():
     from csvplus_b200.dist import allgather_table_nccl, init_comm
     if world > 1:
         init_comm(ctx, dist)  # the library's own communicator: the build-side all-gather runs inside the C ABI
+        dist.barrier()
 
     dbg = bool(os.environ.get("BENCH_DEBUG")) and rank == 0
 
@@ -383,9 +387,10 @@ def main():
         return t
 
     sync0 = [0, 0]
+    per_step = []
 
     def timed(fn, steps, warmup, sampler_dev=None):
-        sampler = ClockSampler(sampler_dev) if sampler_dev is not None else None  # polls through warm-up + timed steps
+        sampler = ClockSampler(sampler_dev) if sampler_dev is not None and not os.environ.get("BENCH_NO_SAMPLER") else None  # polls through warm-up + timed steps
         for _ in range(warmup):
             r = fn(); del r
         ctx.sync(); torch.cuda.synchronize()
@@ -399,13 +404,18 @@ def main():
         t_begin = time.time()
         e0.record(stream)
         rows = 0
+        marks = []
         for _ in range(steps):
             r = fn(); rows = len(r); del r
+            ev = torch.cuda.Event(enable_timing=True); ev.record(stream); marks.append(ev)
         e1.record(stream)
         sync0[1] = ctx.host_syncs() - sync0[0]
         ctx.sync(); torch.cuda.synchronize()
         t_end = time.time()
         ms = e0.elapsed_time(e1)
+        per_step[:] = [round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 3) for i in range(steps)]
+        if os.environ.get("BENCH_DEBUG") or os.environ.get("BENCH_PER_STEP"):
+            print("rank %d per-step ms: %s" % (rank, per_step), file=sys.stderr)
         if world > 1:
             dist.barrier()
             tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -419,6 +429,7 @@ def main():
     # ---------------- device-resident timing (value)
     ms_join, out_rows, st_join, launches, clocks = timed(lambda: join_step(d_cust, d_prod, d_orders), args.steps, args.warmup, local)
     join_syncs = sync0[1] / args.steps
+    join_per_step = list(per_step)
     assert out_rows == ORD_ROWS, (out_rows, ORD_ROWS)  # every order matches exactly one customer and one product
     ms_parse, parse_rows, st_parse, _, _ = timed(lambda: parse_step(d_people), args.steps, args.warmup)
     peak, peak_kind = hbm_peak()
@@ -712,6 +723,8 @@ def main():
                "index_on": {"value": iv, "unit": "rows/s", "sort_seconds": it_sort, "resolve_seconds": it_dedup,
                             "sample": "1 M rows, IndexOn(cust_id,prod_id) + ResolveDuplicates(min order_id), 1 thread"}}
 
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         kernel_ms = sum(v["ms"] for k, v in st_join.items() if not k.startswith(("h2d", "d2h")))
         line = {
@@ -721,7 +734,7 @@ def main():
             "config": workload_config(world),
             "clocks": clocks, "gpu_launches": launches, "out_rows_per_gpu": out_rows,
             "kernel_ms_per_step": kernel_ms / args.steps, "host_gap_ms_per_step": ms_join - kernel_ms / args.steps,
-            "host_syncs_per_step": join_syncs,
+            "host_syncs_per_step": join_syncs, "per_step_ms_rank0": join_per_step,
             "e2e": e2e,
             "roofline": roof(st_join, traffic if world == 1 else None),
             "csv_parse": {"metric": "CSV parse GB/s (configs[1]: parse+SelectColumns(name,surname,id)+Filter(Like name=Amelia))",

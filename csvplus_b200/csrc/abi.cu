@@ -138,6 +138,12 @@ int cpb_init(int device, cpb_ctx** out) {
     try {
         c->device = device;
         CPB_CUDA(cudaSetDevice(device));
+        // CPB_BLOCKING_SYNC=1: host waits sleep on an interrupt instead of spinning.  One process per GPU on a shared host:
+        // N spinning ranks (+ NCCL's proxy threads) can run a cgroup into its CPU quota, and a throttled rank stalls all
+        // the others at the next collective (measured: steps of 55 ms with sporadic 150-750 ms ones at N = 2).
+        if (const char* bs = getenv("CPB_BLOCKING_SYNC")) {
+            if (bs[0] == '1') { cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); cudaGetLastError(); }
+        }
         cudaDeviceProp prop;
         CPB_CUDA(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) throw ArgError{CPB_ERR_UNSUPPORTED, "csvplus_b200 kernels are built for sm_100a only"};

@@ -89,7 +89,16 @@ struct Table {
 // csvplus Index (csvplus.go:610-614, :785-788): rows sorted on `key_cols`.  `table` holds the
 // rows physically in sorted order.  `image` is the order-preserving fixed-width key image
 // (sort.cu) of the sorted rows; `hash*` is the probe table over distinct full keys / key prefixes.
+// "Built on some context's stream": what several contexts may use (the lazily built structures of an index) carries the
+// event recorded after its last kernel; a user makes its own stream wait for it — no host synchronisation.
+struct ReadyEvent {
+    cudaEvent_t ev = nullptr;
+    ~ReadyEvent() { if (ev) cudaEventDestroy(ev); }
+};
+using Ready = std::shared_ptr<ReadyEvent>;
+
 struct HashTable {
+    Ready ready;
     int nkeys = 0;           // number of leading key columns hashed
     uint32_t pbytes = 0;     // image bytes those columns cover
     uint64_t nslots = 0;     // power of two
@@ -105,6 +114,7 @@ struct HashTable {
 // bytes back to back) + one packed word of lengths per row, so that a join fetches an index row with ONE random
 // access instead of two per column.  Built lazily per set of output columns when every value is short.
 struct RowSlots {
+    Ready ready;
     bool usable = false;
     uint32_t S = 0;   // slot bytes (multiple of 16, <= 64)
     Buf slots;        // uint8[nrows][S]
@@ -183,6 +193,14 @@ inline void sync_stream(Ctx* c) {
     c->host_syncs++;
     CPB_CUDA(cudaStreamSynchronize(c->stream));
 }
+
+inline Ready record_ready(Ctx* c) {
+    auto r = std::make_shared<ReadyEvent>();
+    CPB_CUDA(cudaEventCreateWithFlags(&r->ev, cudaEventDisableTiming));
+    CPB_CUDA(cudaEventRecord(r->ev, c->stream));
+    return r;
+}
+inline void wait_ready(Ctx* c, const Ready& r) { if (r && r->ev) CPB_CUDA(cudaStreamWaitEvent(c->stream, r->ev, 0)); }
 
 struct DeviceGuard {  // every entry point: select device, serialise on the ctx
     std::unique_lock<std::mutex> lk;

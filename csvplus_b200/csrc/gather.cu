@@ -438,7 +438,7 @@ static RowSlots& ensure_row_slots(Ctx* c, Index& ix, const std::vector<int>& col
     std::lock_guard<std::mutex> lk(ix.mu);
     auto& smap = by_src ? ix.row_slots_src : ix.row_slots;
     auto it = smap.find(cols);
-    if (it != smap.end()) return it->second;
+    if (it != smap.end()) { wait_ready(c, it->second.ready); return it->second; }
     RowSlots rs;
     // by_src: slot r = source row r (filled sequentially); else sorted order: the sorted rows if they exist, else the source
     // rows through the permutation
@@ -470,7 +470,7 @@ static RowSlots& ensure_row_slots(Ctx* c, Index& ix, const std::vector<int>& col
             rs.usable = true;
         }
     }
-    sync_stream(c);  // complete before another context (stream) can find it in the map
+    rs.ready = record_ready(c);  // another context (stream) that finds it in the map waits for this event, not the host
     return smap.emplace(cols, std::move(rs)).first->second;
 }
 

@@ -191,17 +191,29 @@ __global__ void __launch_bounds__(256) join_probe32_kernel(KeyDesc kd, uint64_t 
 // 16-byte slots for key prefixes <= 12 bytes whose runs all have length 1 (unique keys): four slots per 64-byte
 // DRAM granule at load factor 1/2, so a probe costs about one granule (a 32-byte slot at 2/3 costs about two).
 struct __align__(16) Slot16 { unsigned long long k0; uint32_t k1; uint32_t row1; };  // row1 = sorted row + 1; 0 = empty
+// (a slot is claimed and filled by ONE 128-bit compare-and-swap — SASS ATOMG.E.CAS.128 — so a slot is never seen half
+// written and an insert that meets its own key knows it: `dup`, when given, is set if any key is inserted twice.  That
+// is the whole duplicate check of UniqueIndexOn for keys <= 12 bytes: the second inserter of a key walks the same probe
+// sequence as the first and reaches its slot.)
+__device__ __forceinline__ void cas128(void* addr, unsigned long long vl, unsigned long long vh, unsigned long long& ol, unsigned long long& oh) {
+    asm volatile("{\n.reg .b128 c, v, o;\nmov.b128 c, {%3, %4};\nmov.b128 v, {%5, %6};\natom.global.cas.b128 o, [%2], c, v;\nmov.b128 {%0, %1}, o;\n}"
+                 : "=l"(ol), "=l"(oh) : "l"(addr), "l"(0ull), "l"(0ull), "l"(vl), "l"(vh) : "memory");
+}
 __global__ void hash16_insert_kernel(const uint64_t* __restrict__ image, uint64_t n, uint32_t pbytes, const uint32_t* __restrict__ heads,
-                                     uint64_t nheads, Slot16* slots, uint64_t nslots) {
+                                     uint64_t nheads, Slot16* slots, uint64_t nslots, uint32_t* dup) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nheads) return;
     const uint32_t r = heads[j], full = pbytes >> 3, rem = pbytes & 7;
     unsigned long long w[2] = {0, 0};
     for (uint32_t i = 0; i < full; i++) w[i] = image[(uint64_t)i * n + r];
     if (rem) w[full] = image[(uint64_t)full * n + r] & (~0ull << (8 * (8 - rem)));
+    const unsigned long long lo = w[0], hi = (w[1] >> 32) | ((unsigned long long)(r + 1u) << 32);  // {k0, k1 | row1 << 32}
     uint64_t s = slot_of(hash3(w[0], w[1], 0ull), nslots);
     for (;;) {
-        if (atomicCAS(&slots[s].row1, 0u, r + 1u) == 0u) { slots[s].k0 = w[0]; slots[s].k1 = (uint32_t)(w[1] >> 32); return; }
+        unsigned long long ol, oh;
+        cas128(&slots[s], lo, hi, ol, oh);
+        if ((ol | oh) == 0ull) return;
+        if (dup && ol == lo && (uint32_t)oh == (uint32_t)hi) { *dup = 1u; return; }  // benign race: every writer stores 1
         if (++s == nslots) s = 0;
     }
 }
@@ -255,12 +267,12 @@ __global__ void iota_heads_kernel(uint32_t* heads, uint64_t n) {  // heads[i] = 
 
 // by_src: the table is built over the rows in SOURCE order (a lazily sorted unique index: payload = source row, key
 // image = ix.uimage); otherwise over the sorted order (payload = sorted position, key image = ix.image).
-static HashTable& ensure_hash(Ctx* c, Index& ix, int nk, bool by_src) {
+static HashTable& ensure_hash(Ctx* c, Index& ix, int nk, bool by_src, uint32_t* dup_flag = nullptr) {
     std::lock_guard<std::mutex> lk(ix.mu);
     auto& hmap = by_src ? ix.hash_src : ix.hash;
     const Buf& image = by_src ? ix.uimage : ix.image;
     auto it = hmap.find(nk);
-    if (it != hmap.end()) return it->second;
+    if (it != hmap.end()) { wait_ready(c, it->second.ready); return it->second; }
     HashTable ht;
     ht.nkeys = nk; ht.pbytes = prefix_bytes(ix, nk);
     const uint64_t n = (uint64_t)ix.nrows;
@@ -304,7 +316,7 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk, bool by_src) {
         CPB_CUDA(cudaMemsetAsync(ht.slots16->p, 0, ht.nslots16 * sizeof(Slot16), c->stream));
         KernelTimer kt(c, "hash_build", ht.nheads * (ht.pbytes + 8) + ht.nslots16 * 16);
         hash16_insert_kernel<<<nblk(ht.nheads, 256), 256, 0, c->stream>>>(image->as<uint64_t>(), n, ht.pbytes, ht.heads->as<uint32_t>(), ht.nheads,
-                                                                          ht.slots16->as<Slot16>(), ht.nslots16);
+                                                                          ht.slots16->as<Slot16>(), ht.nslots16, dup_flag);
         CPB_CUDA(cudaGetLastError());
     } else if (ht.pbytes <= 24 && too_large_for_smem) {  // key fits a sector
         ht.nslots32 = ht.nheads + ht.nheads / 2 + 16;
@@ -315,7 +327,7 @@ static HashTable& ensure_hash(Ctx* c, Index& ix, int nk, bool by_src) {
                                                                           ht.slots32->as<Slot32>(), ht.nslots32);
         CPB_CUDA(cudaGetLastError());
     }
-    sync_stream(c);  // complete before any other context (stream) can find it in the map
+    ht.ready = record_ready(c);  // another context (stream) that finds it in the map waits for this event, not the host
     return hmap.emplace(nk, std::move(ht)).first->second;
 }
 
@@ -459,9 +471,16 @@ __global__ void self_check_kernel(const uint32_t* __restrict__ lo, const uint32_
 bool index_has_duplicates(Ctx* c, Index& ix) {
     const uint64_t n = (uint64_t)ix.nrows;
     const int nk = (int)ix.key_cols.size();
-    HashTable& ht = ensure_hash(c, ix, nk, true);
-    Buf lo = dev_alloc(c, n * 4), cnt = dev_alloc(c, (n + 1) * 4), flags = dev_alloc(c, 64);
+    Buf flags = dev_alloc(c, 64);
     CPB_CUDA(cudaMemsetAsync(flags->p, 0, 64, c->stream));
+    HashTable& ht = ensure_hash(c, ix, nk, true, flags->as<uint32_t>() + 8);
+    if (ht.slots16) {  // the 16-byte-slot insert saw every key it met twice: no self probe needed
+        uint32_t* hf = (uint32_t*)c->pinned_scratch(64);
+        CPB_CUDA(cudaMemcpyAsync(hf, flags->p, 64, cudaMemcpyDeviceToHost, c->stream));
+        sync_stream(c);
+        return hf[8] != 0;
+    }
+    Buf lo = dev_alloc(c, n * 4), cnt = dev_alloc(c, (n + 1) * 4);
     probe_dispatch(c, *ix.src, ix.key_col_idx, ix, ht, ix.uimage, nk, lo->as<uint32_t>(), cnt->as<uint32_t>(), flags->as<uint32_t>() + 2);
     {
         KernelTimer kt(c, "unique_check", n * 8);

@@ -15,6 +15,7 @@
 // gathers field bytes.  Records containing quotes (or running past the staged window) take an exact
 // sequential state machine that restates Go's readRecord byte for byte.
 #include <algorithm>
+#include <functional>
 #include <mutex>
 
 #include "core.hpp"
@@ -221,8 +222,60 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
     for (auto& cc : cols) fields.push_back(cc.second);
     std::sort(fields.begin(), fields.end());
     fields.erase(std::unique(fields.begin(), fields.end()), fields.end());
-    if ((int)fields.size() > MAXSEL)
-        throw ArgError{CPB_ERR_UNSUPPORTED, "more than 16 columns in one fused parse; select fewer columns"};
+    if ((int)fields.size() > MAXSEL) {
+        // More than 16 distinct fields (e.g. Take(FromFile(x)) of a wide file, csvplus.go:1160-1168 takes every column):
+        // the scan runs once per group of columns over the same input — each pass extracts its group plus the columns
+        // the predicate compares, so every pass delivers the same rows (and the same error) — and the groups' columns are
+        // put together in the caller's order.  The reference handles any width; so does this, at one read per 16 columns.
+        std::vector<std::string> pred_names;
+        {
+            std::function<void(const cpb_pred*)> walk = [&](const cpb_pred* p) {
+                if (!p) return;
+                if (p->op == CPB_PRED_LIKE) { for (int i = 0; i < p->n; i++) pred_names.push_back(to_string(p->keys[i])); }
+                else for (int i = 0; i < p->n; i++) walk(p->children[i]);
+            };
+            walk(filter);
+        }
+        std::vector<std::pair<std::string, int>> pred_cols;
+        for (auto& cc : cols)
+            if (std::find(pred_names.begin(), pred_names.end(), cc.first) != pred_names.end()) pred_cols.push_back(cc);
+        std::vector<int> pf;
+        for (auto& pc : pred_cols) pf.push_back(pc.second);
+        std::sort(pf.begin(), pf.end()); pf.erase(std::unique(pf.begin(), pf.end()), pf.end());
+        if ((int)pf.size() >= MAXSEL) throw ArgError{CPB_ERR_UNSUPPORTED, "a predicate over 16 or more columns of one fused parse"};
+        auto merged = std::make_shared<Table>();
+        std::vector<Column> out_cols(cols.size());
+        std::vector<char> have(cols.size(), 0);
+        size_t next = 0;
+        bool first_pass = true;
+        while (next < cols.size()) {
+            std::vector<std::pair<std::string, int>> group = pred_cols;
+            std::vector<int> gf = pf;
+            std::vector<size_t> members;
+            for (; next < cols.size(); next++) {
+                if (have[next]) continue;
+                const bool known = std::find(gf.begin(), gf.end(), cols[next].second) != gf.end();
+                if (!known && (int)gf.size() >= MAXSEL) break;
+                if (!known) gf.push_back(cols[next].second);
+                if (std::find_if(group.begin(), group.end(), [&](auto& g) { return g.first == cols[next].first; }) == group.end()) group.push_back(cols[next]);
+                members.push_back(next);
+            }
+            bool he = false; DataError de{};
+            auto part = parse_csv(c, in_arg, n_arg, o_arg, group, filter, &he, &de, sh);
+            if (first_pass) {
+                *had_error = he; *derr = de;
+                merged->ctx = c; merged->nrows = part->nrows; merged->first_line = part->first_line; merged->record_fields = part->record_fields;
+                first_pass = false;
+            } else if (part->nrows != merged->nrows) throw ArgError{CPB_ERR_CUDA, "internal: column groups of one parse disagree on the row count"};
+            for (size_t m : members) {
+                const int k = part->find(cols[m].first);
+                if (k < 0) throw ArgError{CPB_ERR_CUDA, "internal: column group lost a column"};
+                out_cols[m] = part->cols[k]; have[m] = 1;
+            }
+        }
+        for (size_t i = 0; i < cols.size(); i++) { merged->cols.push_back(out_cols[i]); merged->src_field.push_back(cols[i].second); }
+        return merged;
+    }
     std::vector<int> col_slot;
     for (auto& cc : cols) col_slot.push_back((int)(std::lower_bound(fields.begin(), fields.end(), cc.second) - fields.begin()));
     const int nsel = (int)fields.size();
@@ -326,7 +379,7 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
         CPB_CUDA(cudaMemsetAsync(&P.result->err_key, 0xff, 24, c->stream));
         CPB_CUDA(cudaMemsetAsync(P.words, 0, (size_t)P.ntiles * (NP * 8 + 4), c->stream));
         uint64_t algo = n;  // S_in; S_out added by the caller of stats from the totals
-        switch (nsel) {  // kernels specialised on the exact number of extracted columns (no per-column guards)
+        switch (sh ? 99 : nsel) {  // kernels specialised on the exact number of extracted columns (no per-column guards); shards: the guarded one
             case 1: launch_scan<1, true>(c, P, algo); break;
             case 2: launch_scan<2, true>(c, P, algo); break;
             case 3: launch_scan<3, true>(c, P, algo); break;

@@ -386,7 +386,7 @@ struct SlowSink {
     }
 };
 
-struct SlowOut { uint32_t ulen[MAXSEL]; uint32_t present, eq; int nf, err; uint64_t next; };
+struct SlowOut { uint32_t ulen[MAXSEL]; uint32_t present, eq; int nf, err; };
 
 // count mode (emit=false): lengths / predicate terms / error of one record; emit mode: store the unescaped values.
 static __device__ __noinline__ void slow_record(const ParseParams& P, const ByteSrc& src, uint64_t start, bool emit,
@@ -400,7 +400,7 @@ static __device__ __noinline__ void slow_record(const ParseParams& P, const Byte
         }
     }
     SeqResult s = seq_parse_record(src, start, (int)P.delim, sink);
-    o->err = s.err; o->nf = s.nfields; o->present = sink.present; o->eq = sink.eq; o->next = s.next;
+    o->err = s.err; o->nf = s.nfields; o->present = sink.present; o->eq = sink.eq;
     // (shards: a record closed by the end of the buffer instead of a terminator — benign race, every writer stores 1)
     if (!emit && s.err == K_OK && s.next >= src.n && src.n > 0 && src.get(src.n - 1) != '\n') P.result->eof_hit = 1u;
     for (int k = 0; k < P.nsel; k++) o->ulen[k] = ((sink.present >> k) & 1) ? sink.ulen[k] : 0;
@@ -500,7 +500,7 @@ template <int KMAX, bool EXACT, bool HP>
 __device__ __forceinline__ bool generic_record(const ParseParams& P, const ParseSmem& sm, const ByteSrc& src, uint64_t tile_base,
                                                int ws, int rel_n, Rec<KMAX>& r) {
     // empty line: "\n", "\r\n", or a lone "\r" right before EOF
-    if (tile_base + (uint64_t)ws > P.own_end) return false;
+    if (!EXACT && tile_base + (uint64_t)ws > P.own_end) return false;
     int c0 = sm.data[PRE + ws];
     if (c0 == '\n') return false;
     if (c0 == '\r' && (sm.data[PRE + ws + 1] == '\n' || ws + 1 >= rel_n)) return false;
@@ -673,8 +673,9 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
         // ---- chain 1: quote parity at the tile start.  The tile's own parity is published at once; a tile
         // without quotes does not wait for its predecessors here: it proceeds assuming it starts outside
         // quotes and verifies that after pass 1 (the rare miss redoes the tile from `retry`).
-        if (tid == 0) st_release_u32(&P.st1[tile], tile == 0 ? (2u | ((P.pin0 ^ tile_par) << 2)) : (1u | (tile_par << 2)));
-        uint32_t pin = tile == 0 ? P.pin0 : 0;
+        const uint32_t pin0 = EXACT ? 0u : P.pin0;
+        if (tid == 0) st_release_u32(&P.st1[tile], tile == 0 ? (2u | ((pin0 ^ tile_par) << 2)) : (1u | (tile_par << 2)));
+        uint32_t pin = tile == 0 ? pin0 : 0;
         bool pin_known = tile == 0;
         if (hasq && !pin_known) {
             if (warp == 0) {
@@ -774,8 +775,10 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
         // lines 1..m start inside the tile proper (terminator i-1 at position <= TILE-2); line 0 iff first_owned
         const int m_last = (int)sm.wpar[0] - (int)((sm.Tb[TILE_WORDS - 1] >> 31) & 1);
         const int i0 = first_owned ? 0 : 1;
+        // (byte-range shards run the guarded 16-column instantiation only: the kernels specialised on the column count —
+        // the hot ones — carry none of the shard logic; even its few registers cost them 3-5 %)
         int m_last_v = m_last;
-        if (P.own_end != ~0ull && flat_ok)  // a byte-range shard that is not the file's last (uniform, cold, out of line)
+        if (!EXACT && P.own_end != ~0ull && flat_ok)  // a shard that is not the file's last (uniform, cold, out of line)
             m_last_v = shard_tile_tail(P, sm, tile, tile_base, i0, m_last, nterm, rel_n, rel_ds);
         const int nown = m_last_v - i0 + 1;
         const int L = (nown + THREADS - 1) / THREADS;
@@ -796,7 +799,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
                 if (rel_ds > b0) keep = rel_ds >= b0 + 32 ? 0u : (0xffffffffu << (rel_ds - b0));
                 if (rel_n64 < b0 + 32) keep &= rel_n64 <= b0 ? 0u : (0xffffffffu >> (32 - (rel_n64 - b0)));
                 rs[j] &= keep;
-                if (P.ds_is_start && rel_ds >= b0 && rel_ds < b0 + 32 && rel_ds < rel_n64) rs[j] |= 1u << (rel_ds - b0);
+                if ((EXACT || P.ds_is_start) && rel_ds >= b0 && rel_ds < b0 + 32 && rel_ds < rel_n64) rs[j] |= 1u << (rel_ds - b0);
             }
             if (tid == 0 && tile_base == 0 && rel_ds <= 0) rs[0] |= 1u;  // file start
             if (tid == 0) atomicAdd(&P.result->fallback_tiles, 1u);

@@ -46,6 +46,7 @@ def _plain_csv(seed, nrows, ncols=6, crlf_p=0.0, blank_p=0.0, short_p=0.0, long_
     (6, dict(eol_last=False)),
     (7, dict(ncols=3, width=(0, 6))),
     (8, dict(ncols=12, width=(1, 5))),
+    (9, dict(ncols=40, width=(0, 4))),             # more than 16 columns: the scan runs once per group of columns
 ])
 def test_plain_inputs_many_tiles(seed, kw):
     data = _plain_csv(seed, 40_000, **kw)
@@ -54,6 +55,14 @@ def test_plain_inputs_many_tiles(seed, kw):
     sel = ["c%d" % i for i in sorted(random.Random(seed).sample(range(ncols), min(ncols, 1 + seed % 4)))]
     check_parity(data, select=sel)
     check_parity(data)  # every column
+    if ncols > 16:  # every column of a wide file, through a filter, and with an error in the middle
+        vals = orc.reader_rows(data, select=["c1"]).values("c1")
+        common = max(set(vals), key=vals.count)
+        check_parity(data, like={"c1": common.decode(), "c39": ""})
+        lines = data.split(b"\n")
+        lines[len(lines) // 2] = b"short,line"
+        t, orows = check_parity(b"\n".join(lines))
+        assert orows.error is not None and "wrong number of fields" in orows.error
     if ncols >= 2:
         # a predicate that keeps ~ a quarter of the rows: compare against the most frequent value of c1
         vals = orc.reader_rows(data, select=["c1"]).values("c1")

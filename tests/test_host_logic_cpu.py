@@ -93,3 +93,16 @@ def test_predicate_lowering_to_abi_tree():
 def test_error_types_format_like_reference():
     e = cp.DataSourceError(7, "wrong number of fields")
     assert str(e) == "row 7: wrong number of fields" and e.Line == 7
+
+
+def test_go_json_string_escaping():
+    """ToJSON writes strings the way encoding/json does with SetEscapeHTML(false) (csvplus.go:446-474)"""
+    from csvplus_b200.api import _go_json_string as g
+    assert g('plain') == b'"plain"'
+    assert g('q"b\\s') == b'"q\\"b\\\\s"'
+    assert g("a\nb\rc\td\x00e\x1f") == b'"a\\nb\\rc\\td\\u0000e\\u001f"'
+    assert g("<&>") == b'"<&>"'                               # no HTML escaping
+    assert g(" x ") == b'"\\u2028x\\u2029"'          # always escaped
+    assert g("é€𝄞") == "\"é€𝄞\"".encode()                      # valid UTF-8 verbatim
+    assert g(b"\xff\xc3(".decode("utf-8", "surrogateescape")) == b'"\\ufffd\\ufffd("'  # every invalid byte -> U+FFFD
+    assert g(b"\xe2\x82".decode("utf-8", "surrogateescape")) == b'"\\ufffd\\ufffd"'    # truncated sequence
