@@ -344,6 +344,14 @@ def main():
     d_people = ctx.gen_csv("people", (rank * PEOPLE_ROWS, (rank + 1) * PEOPLE_ROWS), seed=SEED, header=True)
     ctx.sync()
 
+    # Python's cyclic collector: a full collection walks every object torch's import created (hundreds of ms) and its
+    # schedule depends only on allocation counts, so it hits every rank at the same step (measured at N = 2: steps of
+    # 55 ms with one of 150-780 ms every ~14 calls).  Everything alive now is long-lived: park it where collections
+    # do not look.
+    import gc
+    gc.collect()
+    gc.freeze()
+
     from csvplus_b200.dist import allgather_table_nccl, init_comm
     if world > 1:
         init_comm(ctx, dist)  # the library's own communicator: the build-side all-gather runs inside the C ABI

@@ -55,23 +55,42 @@ void* Ctx::pinned_scratch(size_t n) {
     return pinned;
 }
 
+// Timing events are recycled: a step launches ~60 timed kernels, and creating / keeping thousands of live events
+// over many steps is not free.  harvest() folds the records whose kernels have already finished into the stats
+// without blocking; drain_events() waits for the rest.
+static void fold_event(Ctx* c, PendingEvent& pe) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, pe.a, pe.b);
+    KStat& s = c->stats[pe.name];
+    s.ms += ms; s.bytes += pe.bytes;
+    c->event_pool.push_back(pe.a); c->event_pool.push_back(pe.b);
+}
+void Ctx::harvest_events() {
+    size_t done = 0;
+    while (done < pending.size() && cudaEventQuery(pending[done].b) == cudaSuccess) { fold_event(this, pending[done]); done++; }
+    cudaGetLastError();  // cudaErrorNotReady of the first unfinished record
+    if (done) pending.erase(pending.begin(), pending.begin() + (long)done);
+}
 void Ctx::drain_events() {
     for (auto& pe : pending) {
         cudaEventSynchronize(pe.b);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, pe.a, pe.b);
-        KStat& s = stats[pe.name];
-        s.ms += ms; s.bytes += pe.bytes;
-        cudaEventDestroy(pe.a); cudaEventDestroy(pe.b);
+        fold_event(this, pe);
     }
     pending.clear();
+}
+static cudaEvent_t take_event(Ctx* c) {
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
 }
 
 KernelTimer::KernelTimer(Ctx* ctx, const char* nm, uint64_t algo_bytes, int launches)
     : c(ctx), on(ctx->stats_on), name(nm), bytes(algo_bytes), nlaunch(launches) {
     c->launches += launches;
     if (on) {
-        cudaEventCreate(&a); cudaEventCreate(&b);
+        if (c->pending.size() >= 64) c->harvest_events();
+        a = take_event(c); b = take_event(c);
         cudaEventRecord(a, c->stream);
     }
 }
@@ -180,6 +199,8 @@ void cpb_shutdown(cpb_ctx* h) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->drain_events();
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    c->event_pool.clear();
     cpb_comm_release(c);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaStreamDestroy(c->stream);

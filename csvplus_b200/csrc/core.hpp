@@ -167,6 +167,7 @@ struct Ctx {
     bool stats_on = false;
     std::map<std::string, KStat> stats;
     std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> event_pool;  // recycled timing events
     uint64_t launches = 0;
     // small pinned scratch for D2H of results
     void* pinned = nullptr; size_t pinned_n = 0;
@@ -178,6 +179,7 @@ struct Ctx {
 
     void* pinned_scratch(size_t n);
     void drain_events();
+    void harvest_events();
 };
 
 // RAII: time a kernel (or a group of launches) on the ctx stream when stats are enabled

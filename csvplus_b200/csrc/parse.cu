@@ -297,6 +297,7 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
     for (int t = 0; t < comp.prog.nterms; t++) P.slot_terms[comp.prog.term_col[t]] |= 1u << t;
     P.ntiles = data_start >= n ? 0 : (uint32_t)((n + TILE - 1) / TILE);
     P.own_end = ~0ull;
+    { static const bool off = getenv("CPB_NO_L2_AHEAD") != nullptr; P.l2_ahead = off ? 0u : 1u; }
     P.ds_is_start = !(sh && sh->index > 0);
     if (sh) {
         P.pin0 = sh->pin0 & 1u;

@@ -31,6 +31,7 @@ struct GenOpts {
     uint8_t delim, comment, lazy, trim;
     uint32_t T[NCLASS];  // transition vector per byte class: bits [3s, 3s+3) = next state from state s
     uint32_t sp_bits[8]; // stand-in bytes of the multi-byte Unicode spaces (subst.cu): white space like ' '
+    uint32_t has_sp;     // any bit of sp_bits set (the per-byte classifier skips the table otherwise)
     const SubTable* subs;
 };
 
@@ -41,7 +42,7 @@ __host__ __device__ inline int gen_class(uint8_t b, const GenOpts& o) {
     if (b == '\r') return C_R;
     if (o.comment && b == o.comment) return C_C;
     if (b == ' ' || b == '\t' || b == '\v' || b == '\f') return C_S;
-    if ((o.sp_bits[b >> 5] >> (b & 31)) & 1u) return C_S;
+    if (o.has_sp && ((o.sp_bits[b >> 5] >> (b & 31)) & 1u)) return C_S;
     return C_O;
 }
 static int gen_delta(int s, int c, bool trim) {
@@ -259,7 +260,11 @@ static inline uint32_t nblk(uint64_t n, int t) { return (uint32_t)((n + t - 1) /
 // Returns the raw pieces of the general parse; parse.cu turns them into a Table and error (shared logic).
 
 static void gen_subs(GenOpts& g, const Substitution* sub) {
-    if (sub && sub->table) { g.subs = sub->table->as<SubTable>(); memcpy(g.sp_bits, sub->host_table.space_bits, sizeof g.sp_bits); }
+    if (sub && sub->table) {
+        g.subs = sub->table->as<SubTable>();
+        memcpy(g.sp_bits, sub->host_table.space_bits, sizeof g.sp_bits);
+        for (int i = 0; i < 8; i++) if (g.sp_bits[i]) g.has_sp = 1;
+    }
 }
 
 void general_header(Ctx* c, const uint8_t* in, uint64_t n, const cpb_reader_opts& o, const Substitution* sub, HeaderOut* dev_out) {

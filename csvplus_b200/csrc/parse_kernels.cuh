@@ -104,6 +104,7 @@ struct ParseParams {
     // byte-range shards of one file (cpb_parse_csv_shard): the quote parity the buffer starts with, and the last byte
     // position at which a record may START to belong to this shard (later ones are the next shard's; ~0: no limit)
     uint32_t pin0;
+    uint32_t l2_ahead;     // 1: prefetch the tile one grid-width ahead into L2
     uint32_t ds_is_start;  // data_start is itself the first byte of a record (after a header row); 0 for shards after the first
     uint64_t own_end;
 };
@@ -630,6 +631,12 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
             fence_proxy_async();
             mbar_expect_tx(&sm.mbar, nbytes);
             bulk_g2s(sm.data + lead, P.in + w_lo, nbytes, &sm.mbar);
+            // the tile one grid-width ahead is taken (by some CTA) about one tile time from now: pull it into L2 so that its
+            // bulk load finds it there
+            if (P.l2_ahead) {
+                const uint64_t pf = tile_base + (uint64_t)gridDim.x * TILE;
+                if (pf + TILE <= (P.n & ~15ull)) bulk_prefetch_l2(P.in + pf, TILE);
+            }
         }
         mbar_wait(&sm.mbar, phase);
         phase ^= 1;

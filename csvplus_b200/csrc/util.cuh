@@ -23,6 +23,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// asks the bulk-copy engine to pull [src, src + bytes) into L2 (no shared memory, no completion to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     asm volatile(
         "{\n"
