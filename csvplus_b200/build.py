@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libcsvplus_b200.so")
 SOURCES = ["abi.cu", "parse.cu", "parse_general.cu", "gather.cu", "sort.cu", "join.cu", "write.cu", "gen.cu", "comm.cu", "subst.cu"]
-HEADERS = ["core.hpp", "util.cuh", "pred.cuh", "parse_kernels.cuh", "parse_lean.cuh", "subst.hpp", os.path.join("..", "..", "include", "csvplus_b200.h")]
+HEADERS = ["core.hpp", "util.cuh", "pred.cuh", "parse_kernels.cuh", "subst.hpp", os.path.join("..", "..", "include", "csvplus_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda"]

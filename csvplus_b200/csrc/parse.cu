@@ -22,7 +22,6 @@
 #include "pred.cuh"
 #include "util.cuh"
 #include "parse_kernels.cuh"
-#include "parse_lean.cuh"
 
 namespace cpb {
 
@@ -68,35 +67,6 @@ template <int KMAX, bool EXACT>
 void launch_scan(Ctx* c, const ParseParams& P, uint64_t algo_bytes) {
     if (EXACT && P.pred.nops == 0) launch_scan_hp<KMAX, EXACT, false>(c, P, algo_bytes);
     else launch_scan_hp<KMAX, EXACT, true>(c, P, algo_bytes);
-}
-
-// the lean kernel (parse_lean.cuh): regular tiles per warp, everything else through the same general tile body
-template <int KMAX, bool HP>
-void launch_lean_hp(Ctx* c, const ParseParams& P, uint64_t algo_bytes) {
-    static std::mutex mu;
-    static int occ_of[64];
-    const size_t smem = ((sizeof(ParseSmem) + 15) & ~size_t(15)) + sizeof(LeanExtra);
-    int occ;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        int& cached = occ_of[c->device & 63];
-        if (cached == 0) {
-            CPB_CUDA(cudaFuncSetAttribute(csv_scan_lean_kernel<KMAX, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int o = 0;
-            CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, csv_scan_lean_kernel<KMAX, HP>, THREADS, smem));
-            cached = o < 1 ? 1 : o;
-        }
-        occ = cached;
-    }
-    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count * occ, P.ntiles);
-    KernelTimer kt(c, "csv_scan", algo_bytes);
-    csv_scan_lean_kernel<KMAX, HP><<<grid, THREADS, smem, c->stream>>>(P);
-    CPB_CUDA(cudaGetLastError());
-}
-template <int KMAX>
-void launch_lean(Ctx* c, const ParseParams& P, uint64_t algo_bytes) {
-    if (P.pred.nops == 0) launch_lean_hp<KMAX, false>(c, P, algo_bytes);
-    else launch_lean_hp<KMAX, true>(c, P, algo_bytes);
 }
 
 }  // namespace
@@ -390,21 +360,6 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
         data_cap[k] = std::min<uint64_t>(data_cap[k], size_class(est, 32u << 20));
     }
 
-    // ---- which scan kernel.  The lean kernel (parse_lean.cuh) handles regular tiles per warp and hands every other tile
-    // to the same general tile body out of line, so it is the choice whenever the sample says regular tiles will dominate:
-    // a fixed field count (the default policy), every selected field inside it, no quote in the sampled windows, and lines
-    // of a length its per-lane row cache and 496-byte look-ahead are sized for.  CPB_SCAN=general|lean overrides (tests).
-    bool use_lean = false;
-    {
-        static const char* force = getenv("CPB_SCAN");
-        const int rc = nsel <= 2 ? 6 : (nsel <= 4 ? 4 : 3);
-        const bool eligible = !sh && !subs_dev && nsel >= 1 && nsel <= 8 && P.expect_fields > 0 && fields.back() < P.expect_fields;
-        const bool likely = h->sample_quotes == 0 && avg >= 4096.0 / (32.0 * rc) * 1.25 && avg <= 200.0;
-        use_lean = eligible && likely;
-        if (force && !strcmp(force, "general")) use_lean = false;
-        if (force && !strcmp(force, "lean")) use_lean = eligible;
-    }
-
     Buf state = dev_alloc(c, (size_t)P.ntiles * (8 + 16ull * NP) + 64 + sizeof(ParseResult));
     std::vector<Buf> offs(nsel), datas(nsel);
     ParseResult res{};
@@ -425,18 +380,6 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
         CPB_CUDA(cudaMemsetAsync(&P.result->err_key, 0xff, 24, c->stream));
         CPB_CUDA(cudaMemsetAsync(P.words, 0, (size_t)P.ntiles * (NP * 8 + 4), c->stream));
         uint64_t algo = n;  // S_in; S_out added by the caller of stats from the totals
-        if (use_lean) {
-            switch (nsel) {
-                case 1: launch_lean<1>(c, P, algo); break;
-                case 2: launch_lean<2>(c, P, algo); break;
-                case 3: launch_lean<3>(c, P, algo); break;
-                case 4: launch_lean<4>(c, P, algo); break;
-                case 5: launch_lean<5>(c, P, algo); break;
-                case 6: launch_lean<6>(c, P, algo); break;
-                case 7: launch_lean<7>(c, P, algo); break;
-                default: launch_lean<8>(c, P, algo); break;
-            }
-        } else
         switch (sh ? 99 : nsel) {  // kernels specialised on the exact number of extracted columns (no per-column guards); shards: the guarded one
             case 1: launch_scan<1, true>(c, P, algo); break;
             case 2: launch_scan<2, true>(c, P, algo); break;
@@ -452,9 +395,6 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
         CPB_CUDA(cudaMemcpyAsync(hr, P.result, sizeof(ParseResult), cudaMemcpyDeviceToHost, c->stream));
         sync_stream(c);
         res = *hr;
-        { static const bool dbg = getenv("CPB_SCAN_DEBUG") != nullptr;
-          if (dbg) fprintf(stderr, "[csv_scan] %s tiles=%u general_tiles=%u dense_fallback=%u rows=%llu\n", use_lean ? "lean" : "general", P.ntiles,
-                           res.general_tiles, res.fallback_tiles, (unsigned long long)res.totals[1]); }
         bool overflow = res.totals[1] > row_cap;
         for (int k = 0; k < nsel; k++) {
             if (res.totals[2 + k] > 0xffffffffull)

@@ -210,7 +210,7 @@ __global__ void g_header_kernel(const uint8_t* in, uint64_t n, GenOpts o, Header
         }
         break;
     }
-    out->truncated = 0; out->rec_start = pos; out->sample_bytes = 0; out->sample_newlines = 0; out->sample_quotes = 0; out->samp_lines = 0;
+    out->truncated = 0; out->rec_start = pos; out->sample_bytes = 0; out->sample_newlines = 0; out->samp_lines = 0;
     if (pos >= n) { out->eof = 1; out->err = 0; out->nfields = 0; out->data_start = n; return; }
     HeaderSink sink{out, o.subs};
     SeqResult r = seq_parse_record_gen(src, pos, o.delim, o.lazy, o.trim, o.sp_bits, sink);

@@ -75,8 +75,6 @@ struct ParseResult {  // device -> host
     unsigned long long first_row_ordinal;  // record ordinal of output row 0 (~0 if no rows)
     uint32_t fallback_tiles;      // tiles that took the dense fallback
     uint32_t eof_hit;             // a record of this shard was closed by the end of the buffer, not by a terminator
-    uint32_t general_tiles;       // lean kernel: tiles that took the general tile body
-    uint32_t pad_;
 };
 
 struct ParseParams {
@@ -188,7 +186,6 @@ struct HeaderOut {
     int32_t truncated;  // names did not fit
     uint64_t rec_start, data_start;
     uint64_t sample_bytes, sample_newlines;
-    unsigned long long sample_quotes;                         // quote bytes seen in the sampled windows (kernel choice only)
     unsigned long long samp_lines;                            // lines split naively for the capacity estimate
     unsigned long long samp_field_bytes[HDR_SAMPLE_FIELDS];   // their bytes per field index
     uint32_t field_len[HDR_MAX_FIELDS];
@@ -210,11 +207,11 @@ struct HeaderSink {
 // in three 64 KiB windows for the row-capacity estimate.  The first 8 KiB are staged in shared memory
 // so that the sequential parse of a normal header never waits on HBM.
 static __global__ void csv_header_kernel(const uint8_t* in, uint64_t n, int delim, const SubTable* subs, HeaderOut* out) {
-    __shared__ unsigned long long s_nl, s_q;
+    __shared__ unsigned long long s_nl;
     __shared__ uint8_t s_head[8192];
     const uint64_t staged = n < 8192 ? n : 8192;
     for (uint64_t i = threadIdx.x; i < staged; i += blockDim.x) s_head[i] = in[i];
-    if (threadIdx.x == 0) { s_nl = 0; s_q = 0; }
+    if (threadIdx.x == 0) s_nl = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         ByteSrc src{in, n, s_head, 0, staged};
@@ -241,7 +238,6 @@ static __global__ void csv_header_kernel(const uint8_t* in, uint64_t n, int deli
     }
     const uint64_t S = 65536;
     unsigned long long cnt = 0, tot = 0;
-    uint32_t qany = 0;
     for (int w = 0; w < 3; w++) {
         uint64_t lo = w == 0 ? 0 : (w == 1 ? (n / 2) : (n > S ? n - S : 0));
         uint64_t hi = lo + S < n ? lo + S : n;
@@ -255,13 +251,11 @@ static __global__ void csv_header_kernel(const uint8_t* in, uint64_t n, int deli
                 const uint4 x = v[i];
                 cnt += __popc(eq_flags(x.x, 0x0a0a0a0au)) + __popc(eq_flags(x.y, 0x0a0a0a0au)) + __popc(eq_flags(x.z, 0x0a0a0a0au)) +
                        __popc(eq_flags(x.w, 0x0a0a0a0au));
-                qany |= eq_any(x.x, 0x22222222u) | eq_any(x.y, 0x22222222u) | eq_any(x.z, 0x22222222u) | eq_any(x.w, 0x22222222u);
             }
             tot += hi16 - lo16;
         }
     }
     atomicAdd(&s_nl, cnt);
-    if (qany) atomicAdd(&s_q, 1ull);
     // mean field lengths: every thread splits one line (naively: quotes ignored — this only sizes buffers) in each window
     __shared__ unsigned long long s_lines, s_fb[HDR_SAMPLE_FIELDS];
     if (threadIdx.x == 0) s_lines = 0;
@@ -288,7 +282,7 @@ static __global__ void csv_header_kernel(const uint8_t* in, uint64_t n, int deli
         else for (int g = 0; g < f && g < HDR_SAMPLE_FIELDS; g++) {}  // partial line: its complete fields stay counted (slight overestimate)
     }
     __syncthreads();
-    if (threadIdx.x == 0) { out->sample_bytes = tot; out->sample_newlines = s_nl; out->sample_quotes = s_q; out->samp_lines = s_lines; }
+    if (threadIdx.x == 0) { out->sample_bytes = tot; out->sample_newlines = s_nl; out->samp_lines = s_lines; }
     if (threadIdx.x < HDR_SAMPLE_FIELDS) out->samp_field_bytes[threadIdx.x] = s_fb[threadIdx.x];
 }
 
@@ -606,467 +600,13 @@ static __device__ __noinline__ int shard_tile_tail(const ParseParams& P, const P
     return m_last_v;
 }
 
-// One staged tile, start to finish: classification, quote chain, flat index, pass 1, block scan + totals chain, pass 2.
-// The window [tile_base - PRE, tile_base + WIN) is already in sm.data.  Called inline by csv_scan_kernel and, out of line,
-// as the cold path of the lean kernel (parse_lean.cuh) for the tiles its fast path declines.
-template <int KMAX, bool EXACT, bool HP>
-__device__ __forceinline__ void general_tile(const ParseParams& P, ParseSmem& sm, const uint32_t tile, const uint8_t* lits, const bool lits_in_smem) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NP = 2 + (EXACT ? KMAX : P.nsel);
-    const uint32_t NL4 = 0x0a0a0a0au, Q4 = 0x22222222u, D4 = P.delim * 0x01010101u;
-    const uint64_t tile_base = (uint64_t)tile * TILE;
-    // bytes at absolute positions >= n are zeroed so that they classify as nothing
-    const int64_t rel_n64 = (int64_t)(P.n - tile_base);  // > 0
-    if (rel_n64 < WIN) {
-        for (int i = (int)rel_n64 + tid; i < WIN + 16; i += THREADS) sm.data[PRE + i] = 0;
-        __syncthreads();
-    }
-    const int rel_n = rel_n64 < WIN ? (int)rel_n64 : WIN;  // also the limit of valid window bytes
-    const bool eof_in_win = rel_n64 < WIN;
-    const int64_t rel_ds = (int64_t)P.data_start - (int64_t)tile_base;
-
-    // ---- classify: newline / structural bitmaps, quote presence
-    const uint4* d4 = reinterpret_cast<const uint4*>(sm.data + PRE);
-    uint16_t* T16 = reinterpret_cast<uint16_t*>(sm.Tb);
-    uint16_t* S16 = reinterpret_cast<uint16_t*>(sm.Sb);
-    uint32_t anyq = 0;
-    for (int v = tid; v < WIN / 16; v += THREADS) {
-        uint4 x = d4[v];
-        uint32_t nl = flags16(eq_flags(x.x, NL4), eq_flags(x.y, NL4), eq_flags(x.z, NL4), eq_flags(x.w, NL4));
-        uint32_t dl = flags16(eq_flags(x.x, D4), eq_flags(x.y, D4), eq_flags(x.z, D4), eq_flags(x.w, D4));
-        T16[v] = (uint16_t)nl;
-        S16[v] = (uint16_t)(dl | nl);
-        anyq |= eq_any(x.x, Q4) | eq_any(x.y, Q4) | eq_any(x.z, Q4) | eq_any(x.w, Q4);
-    }
-    if (tid < 4) { sm.Tb[WIN_WORDS + tid] = 0; sm.Sb[WIN_WORDS + tid] = 0; sm.Qb[WIN_WORDS + tid] = 0; }
-    const bool hasq = __syncthreads_or(anyq != 0);
-    uint32_t tile_par = 0;
-    if (hasq) {
-        uint16_t* Q16 = reinterpret_cast<uint16_t*>(sm.Qb);
-        for (int v = tid; v < WIN / 16; v += THREADS) {
-            uint4 x = d4[v];
-            Q16[v] = (uint16_t)flags16(eq_flags(x.x, Q4), eq_flags(x.y, Q4), eq_flags(x.z, Q4), eq_flags(x.w, Q4));
-        }
-        __syncthreads();
-        uint32_t par = 0;
-        for (int w = tid; w < TILE_WORDS; w += THREADS) par ^= __popc(sm.Qb[w]);
-        tile_par = __syncthreads_count(par & 1) & 1;
-    }
-    // ---- chain 1: quote parity at the tile start.  The tile's own parity is published at once; a tile
-    // without quotes does not wait for its predecessors here: it proceeds assuming it starts outside
-    // quotes and verifies that after pass 1 (the rare miss redoes the tile from `retry`).
-    const uint32_t pin0 = EXACT ? 0u : P.pin0;
-    if (tid == 0) st_release_u32(&P.st1[tile], tile == 0 ? (2u | ((pin0 ^ tile_par) << 2)) : (1u | (tile_par << 2)));
-    uint32_t pin = tile == 0 ? pin0 : 0;
-    bool pin_known = tile == 0;
-    if (hasq && !pin_known) {
-        if (warp == 0) {
-            const uint32_t pv = lookback_parity_w0(P.st1, tile);
-            if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
-        }
-        __syncthreads();
-        pin = sm.pin;
-        pin_known = true;
-    }
-retry:
-    if (hasq || pin) {
-        // in-quote mask by prefix-XOR of the quote bitmap; terminators are newlines outside quotes
-        uint32_t carry = pin;
-        for (int r0 = 0; r0 < WIN_WORDS; r0 += THREADS) {
-            int w = r0 + tid;
-            uint32_t q = (w < WIN_WORDS && hasq) ? sm.Qb[w] : 0;
-            uint32_t px = q; px ^= px << 1; px ^= px << 2; px ^= px << 4; px ^= px << 8; px ^= px << 16;
-            uint32_t bal = __ballot_sync(0xffffffffu, px >> 31);
-            uint32_t before = __popc(bal & lanemask_lt()) & 1;
-            if (lane == 0) sm.wpar[warp] = __popc(bal) & 1;
-            __syncthreads();
-            uint32_t c = carry, tot = 0;
-            for (int i = 0; i < THREADS / 32; i++) { if (i < warp) c ^= sm.wpar[i]; tot ^= sm.wpar[i]; }
-            uint32_t cin = c ^ before;
-            uint32_t iq = (px ^ q) ^ (0u - cin);
-            if (w < WIN_WORDS) sm.Tb[w] &= ~iq;  // (Sb keeps quoted newlines/delimiters: only lines with quotes see them)
-            carry ^= tot;
-            __syncthreads();
-        }
-    }
-    // a virtual terminator at EOF closes a last line that has no newline
-    if (eof_in_win && tid == 0) { sm.Tb[rel_n >> 5] |= 1u << (rel_n & 31); sm.Sb[rel_n >> 5] |= 1u << (rel_n & 31); }
-    if (eof_in_win) __syncthreads();
-
-    // ---- flat structural index
-    uint4 tw = reinterpret_cast<const uint4*>(sm.Tb)[tid];
-    {
-        const uint4 sw = reinterpret_cast<const uint4*>(sm.Sb)[tid];
-        const uint32_t tws[4] = {tw.x, tw.y, tw.z, tw.w}, sws[4] = {sw.x, sw.y, sw.z, sw.w};
-        uint32_t cs = __popc(sw.x) + __popc(sw.y) + __popc(sw.z) + __popc(sw.w);
-        uint32_t ct = __popc(tw.x) + __popc(tw.y) + __popc(tw.z) + __popc(tw.w);
-        uint32_t v = cs | (ct << 16);
-        uint32_t inc = warp_incl_scan(v);
-        if (lane == 31) sm.wtot[0][warp] = inc;
-        // the 64 halo words: one per thread of warps 0-1
-        uint32_t hs = 0, ht = 0, hv = 0, hinc = 0;
-        if (tid < HALO_WORDS) { hs = sm.Sb[TILE_WORDS + tid]; ht = sm.Tb[TILE_WORDS + tid]; hv = __popc(hs) | (__popc(ht) << 16); }
-        if (warp < HALO_WORDS / 32) { hinc = warp_incl_scan(hv); if (lane == 31) sm.wtot[1][warp] = hinc; }
-        __syncthreads();
-        uint32_t ex = inc - v, tile_tot = 0;
-#pragma unroll
-        for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) ex += t; tile_tot += t; }
-        uint32_t o = ex & 0xffffu, tc = ex >> 16;
-        uint32_t halo_tot = 0;
-        for (int i = 0; i < HALO_WORDS / 32; i++) halo_tot += sm.wtot[1][i];
-        // the totals are known before the expansion: a window that does not fit skips it (dense fallback), one
-        // that fits needs no bounds checks
-        const bool fits = (tile_tot & 0xffffu) + (halo_tot & 0xffffu) <= (uint32_t)SCAP && (tile_tot >> 16) + (halo_tot >> 16) <= (uint32_t)LCAP;
-        if (fits) {
-#pragma unroll
-            for (int j = 0; j < WPT; j++) {
-                uint32_t m = sws[j];
-                const int pos0 = (tid * WPT + j) * 32;
-                uint32_t tm = tws[j];
-                while (tm) {  // terminators are ~7x sparser than structurals: their ordinals come from a popcount
-                    int bpos = __ffs(tm) - 1; tm &= tm - 1;
-                    sm.ord[tc++] = (uint16_t)(o + __popc(m & ((1u << bpos) - 1)));
-                }
-                while (m) {
-                    int bpos = __ffs(m) - 1; m &= m - 1;
-                    sm.sidx[o++] = (uint16_t)(pos0 + bpos);
-                }
-            }
-        }
-        if (fits && tid < HALO_WORDS) {
-            uint32_t hex = hinc - hv;
-            for (int i = 0; i < warp; i++) hex += sm.wtot[1][i];
-            uint32_t o2 = (tile_tot & 0xffffu) + (hex & 0xffffu), tc2 = (tile_tot >> 16) + (hex >> 16);
-            uint32_t m = hs;
-            const int pos0 = (TILE_WORDS + tid) * 32;
-            while (m) {
-                int bpos = __ffs(m) - 1; m &= m - 1;
-                sm.sidx[o2] = (uint16_t)(pos0 + bpos);
-                if ((ht >> bpos) & 1) sm.ord[tc2++] = (uint16_t)o2;
-                o2++;
-            }
-        }
-        if (tid == 0) { sm.nstruct = (tile_tot & 0xffffu) + (halo_tot & 0xffffu); sm.nterm = (tile_tot >> 16) + (halo_tot >> 16); }
-        // terminators of the tile proper (tile_tot >> 16) are needed below: stash in wpar[0]
-        if (tid == 0) sm.wpar[0] = tile_tot >> 16;
-        __syncthreads();
-    }
-    const int nterm = (int)sm.nterm;
-    const bool flat_ok = sm.nstruct <= SCAP && sm.nterm <= LCAP;
-    const bool first_owned = tile_base == 0 || (sm.data[PRE - 1] == '\n' && pin == 0);
-    // lines 1..m start inside the tile proper (terminator i-1 at position <= TILE-2); line 0 iff first_owned
-    const int m_last = (int)sm.wpar[0] - (int)((sm.Tb[TILE_WORDS - 1] >> 31) & 1);
-    const int i0 = first_owned ? 0 : 1;
-    // (byte-range shards run the guarded 16-column instantiation only: the kernels specialised on the column count —
-    // the hot ones — carry none of the shard logic; even its few registers cost them 3-5 %)
-    int m_last_v = m_last;
-    if (!EXACT && P.own_end != ~0ull && flat_ok)  // a shard that is not the file's last (uniform, cold, out of line)
-        m_last_v = shard_tile_tail(P, sm, tile, tile_base, i0, m_last, nterm, rel_n, rel_ds);
-    const int nown = m_last_v - i0 + 1;
-    const int L = (nown + THREADS - 1) / THREADS;
-    ByteSrc src{P.in, P.n, sm.data + PRE, tile_base, tile_base + (uint64_t)rel_n};
-
-    // record-start bits of this thread's 4 words (dense fallback only)
-    uint32_t rs[WPT] = {0, 0, 0, 0};
-    if (!flat_ok) {
-        uint32_t prev = tid == 0 ? (first_owned && tile_base > 0 ? 0x80000000u : 0u) : sm.Tb[tid * WPT - 1];
-        rs[0] = (tw.x << 1) | (prev >> 31);
-        rs[1] = (tw.y << 1) | (tw.x >> 31);
-        rs[2] = (tw.z << 1) | (tw.y >> 31);
-        rs[3] = (tw.w << 1) | (tw.z >> 31);
-#pragma unroll
-        for (int j = 0; j < WPT; j++) {
-            const int64_t b0 = (int64_t)(tid * WPT + j) * 32;
-            uint32_t keep = 0xffffffffu;
-            if (rel_ds > b0) keep = rel_ds >= b0 + 32 ? 0u : (0xffffffffu << (rel_ds - b0));
-            if (rel_n64 < b0 + 32) keep &= rel_n64 <= b0 ? 0u : (0xffffffffu >> (32 - (rel_n64 - b0)));
-            rs[j] &= keep;
-            if ((EXACT || P.ds_is_start) && rel_ds >= b0 && rel_ds < b0 + 32 && rel_ds < rel_n64) rs[j] |= 1u << (rel_ds - b0);
-        }
-        if (tid == 0 && tile_base == 0 && rel_ds <= 0) rs[0] |= 1u;  // file start
-        if (tid == 0) atomicAdd(&P.result->fallback_tiles, 1u);
-    }
-
-    // ---- pass 1: count records / surviving rows / bytes per column
-    uint32_t nrec = 0, nrow = 0, cb[KMAX];
-    uint32_t my_err = 0xffffffffu;  // (local record idx << 16) | kind << 8 | slot
-    uint32_t err_rows_local = 0, first_surv_rec = 0;
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) cb[k] = 0;
-    auto account = [&](const Rec<KMAX>& r) -> bool {
-        bool survived = false;
-        if (r.err != K_OK) {
-            if (my_err == 0xffffffffu) { my_err = (nrec << 16) | ((uint32_t)r.err << 8) | (uint32_t)r.err_slot; err_rows_local = nrow; }
-        } else if (!HP || eval_pred(P.pred, r.eq)) {
-            if (nrow == 0) first_surv_rec = nrec;
-            nrow++;
-            survived = true;
-#pragma unroll
-            for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) cb[k] += r.slow ? r.f[k] : (r.f[k] >> 16);
-        }
-        nrec++;
-        return survived;
-    };
-    // pass-1 results of the first RC lines of a thread stay in registers so that pass 2 only writes
-    constexpr int RC = KMAX <= 4 ? 6 : (KMAX <= 8 ? 3 : 1);
-    uint32_t cf[RC][KMAX];
-    uint32_t cmask = 0;
-    bool any_slow = false;
-    if (flat_ok) {
-#pragma unroll
-        for (int q = 0; q < RC; q++) {
-#pragma unroll
-            for (int k = 0; k < KMAX; k++) cf[q][k] = 0;
-            const int i = i0 + tid * L + q;
-            if (q < L && i <= m_last_v) {
-                Rec<KMAX> r;
-                if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
-                    const bool surv = account(r);
-                    if (r.slow) any_slow = true;
-                    else if (surv) {
-                        cmask |= 1u << q;
-#pragma unroll
-                        for (int k = 0; k < KMAX; k++) cf[q][k] = r.f[k];
-                    }
-                }
-            }
-        }
-        for (int q = RC; q < L; q++) {
-            const int i = i0 + tid * L + q;
-            if (i > m_last_v) break;
-            Rec<KMAX> r;
-            if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
-        }
-    } else {
-#pragma unroll 1
-        for (int j = 0; j < WPT; j++) {
-            uint32_t m = rs[j];
-            while (m) {
-                int b = __ffs(m) - 1; m &= m - 1;
-                Rec<KMAX> r;
-                if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, (tid * WPT + j) * 32 + b, rel_n, r)) account(r);
-            }
-        }
-    }
-    if (!pin_known) {  // verify the optimistic assumption "this tile starts outside quotes"
-        if (warp == 0) {
-            const uint32_t pv = lookback_parity_w0(P.st1, tile);
-            if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
-        }
-        __syncthreads();
-        pin = sm.pin;
-        pin_known = true;
-        if (pin) goto retry;
-    }
-    // staged output (coalesced stores) needs every row of the tile cached and on the fast path
-    const bool staged_pre = !__syncthreads_or(any_slow) && flat_ok && L <= RC;
-    // ---- block scan of (records | rows << 16, bytes[k])
-    uint32_t v0 = nrec | (nrow << 16);
-    uint32_t i0s = warp_incl_scan(v0);
-    uint32_t ik[KMAX];
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) ik[k] = warp_incl_scan(cb[k]);
-    if (lane == 31) {
-        sm.wtot[0][warp] = i0s;
-#pragma unroll
-        for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) sm.wtot[1 + k][warp] = ik[k];
-    }
-    __syncthreads();
-    uint32_t ex0 = i0s - v0, tot0 = 0;
-    uint32_t exk[KMAX], totk[KMAX];
-#pragma unroll
-    for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) ex0 += t; tot0 += t; }
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-        exk[k] = 0; totk[k] = 0;
-        if (k < (EXACT ? KMAX : P.nsel)) {
-            exk[k] = ik[k] - cb[k];
-#pragma unroll
-            for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[1 + k][i]; if (i < warp) exk[k] += t; totk[k] += t; }
-        }
-    }
-    const bool staged = staged_pre && (tot0 >> 16) <= (uint32_t)LCAP;
-    // ---- chain 2: global prefix of (records, rows, bytes[k])
-    {
-        unsigned long long mine = 0;  // component `tid` of this tile's totals
-        if (tid == 0) mine = tot0 & 0xffffu;
-        else if (tid == 1) mine = tot0 >> 16;
-#pragma unroll
-        for (int k = 0; k < KMAX; k++) if (tid == 2 + k) mine = totk[k];
-        unsigned long long* wt = P.words + (uint64_t)tile * NP;
-        if (tile == 0) {
-            if (tid < NP) { st_relaxed_u64((uint64_t*)(wt + tid), LB_INCL | mine); sm.tile_prefix[tid] = 0; }
-            __syncthreads();
-        } else {
-            if (tid < NP) st_relaxed_u64((uint64_t*)(wt + tid), LB_AGG | mine);
-            if (warp == 0) {
-                lookback_totals_w0<KMAX>(P.words, tile, NP, sm);
-                if (lane < NP) st_relaxed_u64((uint64_t*)(wt + lane), LB_INCL | (sm.tile_prefix[lane] + mine));
-            }
-            __syncthreads();
-        }
-        if (tile == P.ntiles - 1 && tid < NP) {  // totals + end-of-column sentinels
-            const unsigned long long total = sm.tile_prefix[tid] + mine;
-            P.result->totals[tid] = total;
-            sm.col_total[tid] = total;
-        }
-        if (tile == P.ntiles - 1) {
-            __syncthreads();
-            const unsigned long long rows = sm.col_total[1];
-            if (tid >= 2 && tid < NP && rows <= P.row_cap) P.out_off[tid - 2][rows] = (uint32_t)sm.col_total[tid];
-        }
-    }
-
-    // ---- pass 2: write offsets, gather field bytes
-    {
-        const uint64_t rec0 = sm.tile_prefix[0] + (ex0 & 0xffffu);
-        uint64_t row = sm.tile_prefix[1] + (ex0 >> 16);
-        if (my_err != 0xffffffffu) {
-            unsigned long long key = ((rec0 + (my_err >> 16)) << 16) | (my_err & 0xffffu);
-            atomicMin(&P.result->err_key, key);
-            atomicMin(&P.result->err_rows, (unsigned long long)(row + err_rows_local));
-        }
-        if (staged) {
-            // Tb|Sb|Qb|sidx|ord are dead once pass 1 has cached every row: their 33 KB hold, per column, the
-            // row list (source extent, destination offset) and a staging buffer, so that rows are copied by
-            // all threads evenly and HBM sees full, aligned 16-byte stores.
-            uint32_t* ost = reinterpret_cast<uint32_t*>(sm.Tb);  // [LCAP + 4] destination offsets of the tile's rows
-            uint32_t* wl = ost + (LCAP + 4);                      // [LCAP]     beg | len << 16 of the field
-            uint8_t* stage = reinterpret_cast<uint8_t*>(wl + LCAP);
-            constexpr uint32_t REGION = 3 * (WIN_WORDS + 4) * 4 + SCAP * 2 + LCAP * 2;
-            constexpr uint32_t CH = ((REGION - (2 * LCAP + 4) * 4) / 16) * 16;
-            const uint32_t tile_rows = tot0 >> 16;
-            const uint64_t row_base = sm.tile_prefix[1];
-            const uint32_t osh = (uint32_t)(row_base & 3);
-            if (nrow != 0 && row == 0) P.result->first_row_ordinal = rec0 + first_surv_rec;
-            // (a run-time column loop -- one copy of the staging code instead of KMAX -- measured slower: 679 vs 736 GB/s)
-#pragma unroll
-            for (int k = 0; k < KMAX; k++) {
-                if (k < (EXACT ? KMAX : P.nsel)) {
-                    const uint64_t dbase = sm.tile_prefix[2 + k];
-                    uint32_t myf[RC], exk_k = 0, totk_k = 0;
-#pragma unroll
-                    for (int kk = 0; kk < KMAX; kk++) if (kk == k) { exk_k = exk[kk]; totk_k = totk[kk]; }
-#pragma unroll
-                    for (int q = 0; q < RC; q++) {
-                        myf[q] = 0;
-#pragma unroll
-                        for (int kk = 0; kk < KMAX; kk++) if (kk == k) myf[q] = cf[q][kk];
-                    }
-                    {
-                        uint32_t j = ex0 >> 16, run = exk_k;
-#pragma unroll
-                        for (int q = 0; q < RC; q++)
-                            if ((cmask >> q) & 1) { ost[osh + j] = (uint32_t)(dbase + run); wl[j] = myf[q]; j++; run += myf[q] >> 16; }
-                    }
-                    __syncthreads();
-                    // ---- offsets of this tile's rows
-                    {
-                        uint32_t* gout = P.out_off[k] + (row_base - osh);
-                        const uint64_t rows_ok = P.row_cap > row_base ? P.row_cap - row_base : 0;  // rows of this tile that fit
-                        const uint32_t lim_e = osh + (uint32_t)(tile_rows < rows_ok ? tile_rows : rows_ok);
-                        for (uint32_t e = tid * 4; e < lim_e; e += THREADS * 4)
-                            if (e >= osh && e + 4 <= lim_e) *reinterpret_cast<uint4*>(gout + e) = *reinterpret_cast<const uint4*>(ost + e);
-                        if (tid < 8) {  // partial first / last vector: one element per lane
-                            const uint32_t tv0 = lim_e & ~3u;
-                            const uint32_t x = tid < 4 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 4);
-                            const bool head = tid < 4 && osh != 0;
-                            const bool tail = tid >= 4 && (lim_e & 3u) != 0 && !(tv0 == 0 && osh != 0);
-                            if ((head || tail) && x >= osh && x < lim_e) gout[x] = ost[x];
-                        }
-                    }
-                    // ---- field bytes
-                    const uint32_t B = totk_k;
-                    const uint32_t r16 = (uint32_t)(dbase & 15);
-                    const uint64_t room = P.data_cap[k] > dbase ? P.data_cap[k] - dbase : 0;
-                    const uint32_t hi_ok = r16 + (uint32_t)(B < room ? B : room);  // shifted local end of writable bytes
-                    uint8_t* gbase = P.out_data[k] + (dbase - r16);
-                    for (uint32_t c0 = 0; c0 < r16 + B; c0 += CH) {
-                        for (uint32_t j = tid; j < tile_rows; j += THREADS) {
-                            const uint32_t f = wl[j], len = f >> 16;
-                            const uint32_t st = ost[osh + j] - (uint32_t)dbase + r16;  // shifted tile-local start
-                            const uint32_t lo = st > c0 ? st : c0, hi = st + len < c0 + CH ? st + len : c0 + CH;
-                            const uint8_t* sp = sm.data + PRE + (f & 0xffffu) - st;
-                            for (uint32_t x = lo; x < hi; x++) stage[x - c0] = sp[x];  // (word-wise copies measured slower)
-                        }
-                        __syncthreads();
-                        const uint32_t cend = c0 + CH < r16 + B ? c0 + CH : r16 + B;
-                        for (uint32_t x0 = c0 + tid * 16; x0 < cend; x0 += THREADS * 16)
-                            if (x0 >= r16 && x0 + 16 <= hi_ok) *reinterpret_cast<uint4*>(gbase + x0) = *reinterpret_cast<const uint4*>(stage + (x0 - c0));
-                        // the (at most two) partial vectors at the column's first and last byte: one byte per lane
-                        if (tid < 32) {
-                            const uint32_t tv0 = hi_ok & ~15u;
-                            const uint32_t x = tid < 16 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 16);
-                            const bool head = tid < 16 && c0 == 0 && r16 != 0;
-                            const bool tail = tid >= 16 && (hi_ok & 15u) != 0 && tv0 >= c0 && tv0 < cend && !(tv0 == 0 && r16 != 0);
-                            if ((head || tail) && x >= r16 && x < hi_ok) gbase[x] = stage[x - c0];
-                        }
-                        __syncthreads();
-                    }
-                    __syncthreads();
-                }
-            }
-        } else if (nrow != 0) {
-            uint64_t off[KMAX];
-#pragma unroll
-            for (int k = 0; k < KMAX; k++) off[k] = k < (EXACT ? KMAX : P.nsel) ? sm.tile_prefix[2 + k] + exk[k] : 0;
-            uint32_t rec_local = 0;
-            auto emit = [&](const Rec<KMAX>& r, uint64_t start_abs) {
-                if (r.err != K_OK || (HP && !eval_pred(P.pred, r.eq))) { rec_local++; return; }
-                if (row == 0) P.result->first_row_ordinal = rec0 + rec_local;
-                const bool row_ok = row < P.row_cap;
-                if (r.slow) {
-                    uint64_t dst_off[MAXSEL];
-                    uint32_t maxlen[MAXSEL];
-                    SlowOut so;
-#pragma unroll
-                    for (int k = 0; k < KMAX; k++) { dst_off[k] = off[k]; maxlen[k] = r.f[k]; }
-                    slow_record(P, src, start_abs, true, dst_off, maxlen, &so);
-                }
-#pragma unroll
-                for (int k = 0; k < KMAX; k++) {
-                    if (k < (EXACT ? KMAX : P.nsel)) {
-                        uint32_t len = r.slow ? r.f[k] : (r.f[k] >> 16);
-                        if (row_ok) P.out_off[k][row] = (uint32_t)off[k];
-                        if (!r.slow && off[k] + len <= P.data_cap[k]) {
-                            const uint8_t* s = sm.data + PRE + (r.f[k] & 0xffffu);
-                            uint8_t* d = P.out_data[k] + off[k];
-                            for (uint32_t i = 0; i < len; i++) d[i] = s[i];
-                        }
-                        off[k] += len;
-                    }
-                }
-                row++; rec_local++;
-            };
-            if (flat_ok) {
-                for (int q = 0; q < L; q++) {
-                    const int i = i0 + tid * L + q;
-                    if (i > m_last_v) break;
-                    Rec<KMAX> r;
-                    if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
-                        emit(r, tile_base + (i == 0 ? 0 : (uint64_t)sm.sidx[sm.ord[i - 1]] + 1));
-                }
-            } else {
-#pragma unroll 1
-                for (int j = 0; j < WPT; j++) {
-                    uint32_t m = rs[j];
-                    while (m) {
-                        int b = __ffs(m) - 1; m &= m - 1;
-                        const int ws = (tid * WPT + j) * 32 + b;
-                        Rec<KMAX> r;
-                        if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, ws, rel_n, r)) emit(r, tile_base + ws);
-                    }
-                }
-            }
-        }
-    }
-}
-
 template <int KMAX, bool EXACT, bool HP>
 __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_scan_kernel(const __grid_constant__ ParseParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ParseSmem& sm = *reinterpret_cast<ParseSmem*>(smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NP = 2 + (EXACT ? KMAX : P.nsel);
+    const uint32_t NL4 = 0x0a0a0a0au, Q4 = 0x22222222u, D4 = P.delim * 0x01010101u;
 
     if (tid == 0) { mbar_init(&sm.mbar, 1); fence_mbar_init(); }
     const bool lits_in_smem = P.lits_len <= LITS_SMEM;
@@ -1100,7 +640,451 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
         }
         mbar_wait(&sm.mbar, phase);
         phase ^= 1;
-        general_tile<KMAX, EXACT, HP>(P, sm, tile, lits, lits_in_smem);
+        // bytes at absolute positions >= n are zeroed so that they classify as nothing
+        const int64_t rel_n64 = (int64_t)(P.n - tile_base);  // > 0
+        if (rel_n64 < WIN) {
+            for (int i = (int)rel_n64 + tid; i < WIN + 16; i += THREADS) sm.data[PRE + i] = 0;
+            __syncthreads();
+        }
+        const int rel_n = rel_n64 < WIN ? (int)rel_n64 : WIN;  // also the limit of valid window bytes
+        const bool eof_in_win = rel_n64 < WIN;
+        const int64_t rel_ds = (int64_t)P.data_start - (int64_t)tile_base;
+
+        // ---- classify: newline / structural bitmaps, quote presence
+        const uint4* d4 = reinterpret_cast<const uint4*>(sm.data + PRE);
+        uint16_t* T16 = reinterpret_cast<uint16_t*>(sm.Tb);
+        uint16_t* S16 = reinterpret_cast<uint16_t*>(sm.Sb);
+        uint32_t anyq = 0;
+        for (int v = tid; v < WIN / 16; v += THREADS) {
+            uint4 x = d4[v];
+            uint32_t nl = flags16(eq_flags(x.x, NL4), eq_flags(x.y, NL4), eq_flags(x.z, NL4), eq_flags(x.w, NL4));
+            uint32_t dl = flags16(eq_flags(x.x, D4), eq_flags(x.y, D4), eq_flags(x.z, D4), eq_flags(x.w, D4));
+            T16[v] = (uint16_t)nl;
+            S16[v] = (uint16_t)(dl | nl);
+            anyq |= eq_any(x.x, Q4) | eq_any(x.y, Q4) | eq_any(x.z, Q4) | eq_any(x.w, Q4);
+        }
+        if (tid < 4) { sm.Tb[WIN_WORDS + tid] = 0; sm.Sb[WIN_WORDS + tid] = 0; sm.Qb[WIN_WORDS + tid] = 0; }
+        const bool hasq = __syncthreads_or(anyq != 0);
+        uint32_t tile_par = 0;
+        if (hasq) {
+            uint16_t* Q16 = reinterpret_cast<uint16_t*>(sm.Qb);
+            for (int v = tid; v < WIN / 16; v += THREADS) {
+                uint4 x = d4[v];
+                Q16[v] = (uint16_t)flags16(eq_flags(x.x, Q4), eq_flags(x.y, Q4), eq_flags(x.z, Q4), eq_flags(x.w, Q4));
+            }
+            __syncthreads();
+            uint32_t par = 0;
+            for (int w = tid; w < TILE_WORDS; w += THREADS) par ^= __popc(sm.Qb[w]);
+            tile_par = __syncthreads_count(par & 1) & 1;
+        }
+        // ---- chain 1: quote parity at the tile start.  The tile's own parity is published at once; a tile
+        // without quotes does not wait for its predecessors here: it proceeds assuming it starts outside
+        // quotes and verifies that after pass 1 (the rare miss redoes the tile from `retry`).
+        const uint32_t pin0 = EXACT ? 0u : P.pin0;
+        if (tid == 0) st_release_u32(&P.st1[tile], tile == 0 ? (2u | ((pin0 ^ tile_par) << 2)) : (1u | (tile_par << 2)));
+        uint32_t pin = tile == 0 ? pin0 : 0;
+        bool pin_known = tile == 0;
+        if (hasq && !pin_known) {
+            if (warp == 0) {
+                const uint32_t pv = lookback_parity_w0(P.st1, tile);
+                if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
+            }
+            __syncthreads();
+            pin = sm.pin;
+            pin_known = true;
+        }
+    retry:
+        if (hasq || pin) {
+            // in-quote mask by prefix-XOR of the quote bitmap; terminators are newlines outside quotes
+            uint32_t carry = pin;
+            for (int r0 = 0; r0 < WIN_WORDS; r0 += THREADS) {
+                int w = r0 + tid;
+                uint32_t q = (w < WIN_WORDS && hasq) ? sm.Qb[w] : 0;
+                uint32_t px = q; px ^= px << 1; px ^= px << 2; px ^= px << 4; px ^= px << 8; px ^= px << 16;
+                uint32_t bal = __ballot_sync(0xffffffffu, px >> 31);
+                uint32_t before = __popc(bal & lanemask_lt()) & 1;
+                if (lane == 0) sm.wpar[warp] = __popc(bal) & 1;
+                __syncthreads();
+                uint32_t c = carry, tot = 0;
+                for (int i = 0; i < THREADS / 32; i++) { if (i < warp) c ^= sm.wpar[i]; tot ^= sm.wpar[i]; }
+                uint32_t cin = c ^ before;
+                uint32_t iq = (px ^ q) ^ (0u - cin);
+                if (w < WIN_WORDS) sm.Tb[w] &= ~iq;  // (Sb keeps quoted newlines/delimiters: only lines with quotes see them)
+                carry ^= tot;
+                __syncthreads();
+            }
+        }
+        // a virtual terminator at EOF closes a last line that has no newline
+        if (eof_in_win && tid == 0) { sm.Tb[rel_n >> 5] |= 1u << (rel_n & 31); sm.Sb[rel_n >> 5] |= 1u << (rel_n & 31); }
+        if (eof_in_win) __syncthreads();
+
+        // ---- flat structural index
+        uint4 tw = reinterpret_cast<const uint4*>(sm.Tb)[tid];
+        {
+            const uint4 sw = reinterpret_cast<const uint4*>(sm.Sb)[tid];
+            const uint32_t tws[4] = {tw.x, tw.y, tw.z, tw.w}, sws[4] = {sw.x, sw.y, sw.z, sw.w};
+            uint32_t cs = __popc(sw.x) + __popc(sw.y) + __popc(sw.z) + __popc(sw.w);
+            uint32_t ct = __popc(tw.x) + __popc(tw.y) + __popc(tw.z) + __popc(tw.w);
+            uint32_t v = cs | (ct << 16);
+            uint32_t inc = warp_incl_scan(v);
+            if (lane == 31) sm.wtot[0][warp] = inc;
+            // the 64 halo words: one per thread of warps 0-1
+            uint32_t hs = 0, ht = 0, hv = 0, hinc = 0;
+            if (tid < HALO_WORDS) { hs = sm.Sb[TILE_WORDS + tid]; ht = sm.Tb[TILE_WORDS + tid]; hv = __popc(hs) | (__popc(ht) << 16); }
+            if (warp < HALO_WORDS / 32) { hinc = warp_incl_scan(hv); if (lane == 31) sm.wtot[1][warp] = hinc; }
+            __syncthreads();
+            uint32_t ex = inc - v, tile_tot = 0;
+#pragma unroll
+            for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) ex += t; tile_tot += t; }
+            uint32_t o = ex & 0xffffu, tc = ex >> 16;
+            uint32_t halo_tot = 0;
+            for (int i = 0; i < HALO_WORDS / 32; i++) halo_tot += sm.wtot[1][i];
+            // the totals are known before the expansion: a window that does not fit skips it (dense fallback), one
+            // that fits needs no bounds checks
+            const bool fits = (tile_tot & 0xffffu) + (halo_tot & 0xffffu) <= (uint32_t)SCAP && (tile_tot >> 16) + (halo_tot >> 16) <= (uint32_t)LCAP;
+            if (fits) {
+#pragma unroll
+                for (int j = 0; j < WPT; j++) {
+                    uint32_t m = sws[j];
+                    const int pos0 = (tid * WPT + j) * 32;
+                    uint32_t tm = tws[j];
+                    while (tm) {  // terminators are ~7x sparser than structurals: their ordinals come from a popcount
+                        int bpos = __ffs(tm) - 1; tm &= tm - 1;
+                        sm.ord[tc++] = (uint16_t)(o + __popc(m & ((1u << bpos) - 1)));
+                    }
+                    while (m) {
+                        int bpos = __ffs(m) - 1; m &= m - 1;
+                        sm.sidx[o++] = (uint16_t)(pos0 + bpos);
+                    }
+                }
+            }
+            if (fits && tid < HALO_WORDS) {
+                uint32_t hex = hinc - hv;
+                for (int i = 0; i < warp; i++) hex += sm.wtot[1][i];
+                uint32_t o2 = (tile_tot & 0xffffu) + (hex & 0xffffu), tc2 = (tile_tot >> 16) + (hex >> 16);
+                uint32_t m = hs;
+                const int pos0 = (TILE_WORDS + tid) * 32;
+                while (m) {
+                    int bpos = __ffs(m) - 1; m &= m - 1;
+                    sm.sidx[o2] = (uint16_t)(pos0 + bpos);
+                    if ((ht >> bpos) & 1) sm.ord[tc2++] = (uint16_t)o2;
+                    o2++;
+                }
+            }
+            if (tid == 0) { sm.nstruct = (tile_tot & 0xffffu) + (halo_tot & 0xffffu); sm.nterm = (tile_tot >> 16) + (halo_tot >> 16); }
+            // terminators of the tile proper (tile_tot >> 16) are needed below: stash in wpar[0]
+            if (tid == 0) sm.wpar[0] = tile_tot >> 16;
+            __syncthreads();
+        }
+        const int nterm = (int)sm.nterm;
+        const bool flat_ok = sm.nstruct <= SCAP && sm.nterm <= LCAP;
+        const bool first_owned = tile_base == 0 || (sm.data[PRE - 1] == '\n' && pin == 0);
+        // lines 1..m start inside the tile proper (terminator i-1 at position <= TILE-2); line 0 iff first_owned
+        const int m_last = (int)sm.wpar[0] - (int)((sm.Tb[TILE_WORDS - 1] >> 31) & 1);
+        const int i0 = first_owned ? 0 : 1;
+        // (byte-range shards run the guarded 16-column instantiation only: the kernels specialised on the column count —
+        // the hot ones — carry none of the shard logic; even its few registers cost them 3-5 %)
+        int m_last_v = m_last;
+        if (!EXACT && P.own_end != ~0ull && flat_ok)  // a shard that is not the file's last (uniform, cold, out of line)
+            m_last_v = shard_tile_tail(P, sm, tile, tile_base, i0, m_last, nterm, rel_n, rel_ds);
+        const int nown = m_last_v - i0 + 1;
+        const int L = (nown + THREADS - 1) / THREADS;
+        ByteSrc src{P.in, P.n, sm.data + PRE, tile_base, tile_base + (uint64_t)rel_n};
+
+        // record-start bits of this thread's 4 words (dense fallback only)
+        uint32_t rs[WPT] = {0, 0, 0, 0};
+        if (!flat_ok) {
+            uint32_t prev = tid == 0 ? (first_owned && tile_base > 0 ? 0x80000000u : 0u) : sm.Tb[tid * WPT - 1];
+            rs[0] = (tw.x << 1) | (prev >> 31);
+            rs[1] = (tw.y << 1) | (tw.x >> 31);
+            rs[2] = (tw.z << 1) | (tw.y >> 31);
+            rs[3] = (tw.w << 1) | (tw.z >> 31);
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                const int64_t b0 = (int64_t)(tid * WPT + j) * 32;
+                uint32_t keep = 0xffffffffu;
+                if (rel_ds > b0) keep = rel_ds >= b0 + 32 ? 0u : (0xffffffffu << (rel_ds - b0));
+                if (rel_n64 < b0 + 32) keep &= rel_n64 <= b0 ? 0u : (0xffffffffu >> (32 - (rel_n64 - b0)));
+                rs[j] &= keep;
+                if ((EXACT || P.ds_is_start) && rel_ds >= b0 && rel_ds < b0 + 32 && rel_ds < rel_n64) rs[j] |= 1u << (rel_ds - b0);
+            }
+            if (tid == 0 && tile_base == 0 && rel_ds <= 0) rs[0] |= 1u;  // file start
+            if (tid == 0) atomicAdd(&P.result->fallback_tiles, 1u);
+        }
+
+        // ---- pass 1: count records / surviving rows / bytes per column
+        uint32_t nrec = 0, nrow = 0, cb[KMAX];
+        uint32_t my_err = 0xffffffffu;  // (local record idx << 16) | kind << 8 | slot
+        uint32_t err_rows_local = 0, first_surv_rec = 0;
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) cb[k] = 0;
+        auto account = [&](const Rec<KMAX>& r) -> bool {
+            bool survived = false;
+            if (r.err != K_OK) {
+                if (my_err == 0xffffffffu) { my_err = (nrec << 16) | ((uint32_t)r.err << 8) | (uint32_t)r.err_slot; err_rows_local = nrow; }
+            } else if (!HP || eval_pred(P.pred, r.eq)) {
+                if (nrow == 0) first_surv_rec = nrec;
+                nrow++;
+                survived = true;
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) cb[k] += r.slow ? r.f[k] : (r.f[k] >> 16);
+            }
+            nrec++;
+            return survived;
+        };
+        // pass-1 results of the first RC lines of a thread stay in registers so that pass 2 only writes
+        constexpr int RC = KMAX <= 4 ? 6 : (KMAX <= 8 ? 3 : 1);
+        uint32_t cf[RC][KMAX];
+        uint32_t cmask = 0;
+        bool any_slow = false;
+        if (flat_ok) {
+#pragma unroll
+            for (int q = 0; q < RC; q++) {
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) cf[q][k] = 0;
+                const int i = i0 + tid * L + q;
+                if (q < L && i <= m_last_v) {
+                    Rec<KMAX> r;
+                    if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) {
+                        const bool surv = account(r);
+                        if (r.slow) any_slow = true;
+                        else if (surv) {
+                            cmask |= 1u << q;
+#pragma unroll
+                            for (int k = 0; k < KMAX; k++) cf[q][k] = r.f[k];
+                        }
+                    }
+                }
+            }
+            for (int q = RC; q < L; q++) {
+                const int i = i0 + tid * L + q;
+                if (i > m_last_v) break;
+                Rec<KMAX> r;
+                if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r)) account(r);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < WPT; j++) {
+                uint32_t m = rs[j];
+                while (m) {
+                    int b = __ffs(m) - 1; m &= m - 1;
+                    Rec<KMAX> r;
+                    if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, (tid * WPT + j) * 32 + b, rel_n, r)) account(r);
+                }
+            }
+        }
+        if (!pin_known) {  // verify the optimistic assumption "this tile starts outside quotes"
+            if (warp == 0) {
+                const uint32_t pv = lookback_parity_w0(P.st1, tile);
+                if (lane == 0) { sm.pin = pv; st_release_u32(&P.st1[tile], 2u | ((pv ^ tile_par) << 2)); }
+            }
+            __syncthreads();
+            pin = sm.pin;
+            pin_known = true;
+            if (pin) goto retry;
+        }
+        // staged output (coalesced stores) needs every row of the tile cached and on the fast path
+        const bool staged_pre = !__syncthreads_or(any_slow) && flat_ok && L <= RC;
+        // ---- block scan of (records | rows << 16, bytes[k])
+        uint32_t v0 = nrec | (nrow << 16);
+        uint32_t i0s = warp_incl_scan(v0);
+        uint32_t ik[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) ik[k] = warp_incl_scan(cb[k]);
+        if (lane == 31) {
+            sm.wtot[0][warp] = i0s;
+#pragma unroll
+            for (int k = 0; k < KMAX; k++) if (k < (EXACT ? KMAX : P.nsel)) sm.wtot[1 + k][warp] = ik[k];
+        }
+        __syncthreads();
+        uint32_t ex0 = i0s - v0, tot0 = 0;
+        uint32_t exk[KMAX], totk[KMAX];
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[0][i]; if (i < warp) ex0 += t; tot0 += t; }
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+            exk[k] = 0; totk[k] = 0;
+            if (k < (EXACT ? KMAX : P.nsel)) {
+                exk[k] = ik[k] - cb[k];
+#pragma unroll
+                for (int i = 0; i < THREADS / 32; i++) { uint32_t t = sm.wtot[1 + k][i]; if (i < warp) exk[k] += t; totk[k] += t; }
+            }
+        }
+        const bool staged = staged_pre && (tot0 >> 16) <= (uint32_t)LCAP;
+        // ---- chain 2: global prefix of (records, rows, bytes[k])
+        {
+            unsigned long long mine = 0;  // component `tid` of this tile's totals
+            if (tid == 0) mine = tot0 & 0xffffu;
+            else if (tid == 1) mine = tot0 >> 16;
+#pragma unroll
+            for (int k = 0; k < KMAX; k++) if (tid == 2 + k) mine = totk[k];
+            unsigned long long* wt = P.words + (uint64_t)tile * NP;
+            if (tile == 0) {
+                if (tid < NP) { st_relaxed_u64((uint64_t*)(wt + tid), LB_INCL | mine); sm.tile_prefix[tid] = 0; }
+                __syncthreads();
+            } else {
+                if (tid < NP) st_relaxed_u64((uint64_t*)(wt + tid), LB_AGG | mine);
+                if (warp == 0) {
+                    lookback_totals_w0<KMAX>(P.words, tile, NP, sm);
+                    if (lane < NP) st_relaxed_u64((uint64_t*)(wt + lane), LB_INCL | (sm.tile_prefix[lane] + mine));
+                }
+                __syncthreads();
+            }
+            if (tile == P.ntiles - 1 && tid < NP) {  // totals + end-of-column sentinels
+                const unsigned long long total = sm.tile_prefix[tid] + mine;
+                P.result->totals[tid] = total;
+                sm.col_total[tid] = total;
+            }
+            if (tile == P.ntiles - 1) {
+                __syncthreads();
+                const unsigned long long rows = sm.col_total[1];
+                if (tid >= 2 && tid < NP && rows <= P.row_cap) P.out_off[tid - 2][rows] = (uint32_t)sm.col_total[tid];
+            }
+        }
+
+        // ---- pass 2: write offsets, gather field bytes
+        {
+            const uint64_t rec0 = sm.tile_prefix[0] + (ex0 & 0xffffu);
+            uint64_t row = sm.tile_prefix[1] + (ex0 >> 16);
+            if (my_err != 0xffffffffu) {
+                unsigned long long key = ((rec0 + (my_err >> 16)) << 16) | (my_err & 0xffffu);
+                atomicMin(&P.result->err_key, key);
+                atomicMin(&P.result->err_rows, (unsigned long long)(row + err_rows_local));
+            }
+            if (staged) {
+                // Tb|Sb|Qb|sidx|ord are dead once pass 1 has cached every row: their 33 KB hold, per column, the
+                // row list (source extent, destination offset) and a staging buffer, so that rows are copied by
+                // all threads evenly and HBM sees full, aligned 16-byte stores.
+                uint32_t* ost = reinterpret_cast<uint32_t*>(sm.Tb);  // [LCAP + 4] destination offsets of the tile's rows
+                uint32_t* wl = ost + (LCAP + 4);                      // [LCAP]     beg | len << 16 of the field
+                uint8_t* stage = reinterpret_cast<uint8_t*>(wl + LCAP);
+                constexpr uint32_t REGION = 3 * (WIN_WORDS + 4) * 4 + SCAP * 2 + LCAP * 2;
+                constexpr uint32_t CH = ((REGION - (2 * LCAP + 4) * 4) / 16) * 16;
+                const uint32_t tile_rows = tot0 >> 16;
+                const uint64_t row_base = sm.tile_prefix[1];
+                const uint32_t osh = (uint32_t)(row_base & 3);
+                if (nrow != 0 && row == 0) P.result->first_row_ordinal = rec0 + first_surv_rec;
+                // (a run-time column loop -- one copy of the staging code instead of KMAX -- measured slower: 679 vs 736 GB/s)
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) {
+                    if (k < (EXACT ? KMAX : P.nsel)) {
+                        const uint64_t dbase = sm.tile_prefix[2 + k];
+                        uint32_t myf[RC], exk_k = 0, totk_k = 0;
+#pragma unroll
+                        for (int kk = 0; kk < KMAX; kk++) if (kk == k) { exk_k = exk[kk]; totk_k = totk[kk]; }
+#pragma unroll
+                        for (int q = 0; q < RC; q++) {
+                            myf[q] = 0;
+#pragma unroll
+                            for (int kk = 0; kk < KMAX; kk++) if (kk == k) myf[q] = cf[q][kk];
+                        }
+                        {
+                            uint32_t j = ex0 >> 16, run = exk_k;
+#pragma unroll
+                            for (int q = 0; q < RC; q++)
+                                if ((cmask >> q) & 1) { ost[osh + j] = (uint32_t)(dbase + run); wl[j] = myf[q]; j++; run += myf[q] >> 16; }
+                        }
+                        __syncthreads();
+                        // ---- offsets of this tile's rows
+                        {
+                            uint32_t* gout = P.out_off[k] + (row_base - osh);
+                            const uint64_t rows_ok = P.row_cap > row_base ? P.row_cap - row_base : 0;  // rows of this tile that fit
+                            const uint32_t lim_e = osh + (uint32_t)(tile_rows < rows_ok ? tile_rows : rows_ok);
+                            for (uint32_t e = tid * 4; e < lim_e; e += THREADS * 4)
+                                if (e >= osh && e + 4 <= lim_e) *reinterpret_cast<uint4*>(gout + e) = *reinterpret_cast<const uint4*>(ost + e);
+                            if (tid < 8) {  // partial first / last vector: one element per lane
+                                const uint32_t tv0 = lim_e & ~3u;
+                                const uint32_t x = tid < 4 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 4);
+                                const bool head = tid < 4 && osh != 0;
+                                const bool tail = tid >= 4 && (lim_e & 3u) != 0 && !(tv0 == 0 && osh != 0);
+                                if ((head || tail) && x >= osh && x < lim_e) gout[x] = ost[x];
+                            }
+                        }
+                        // ---- field bytes
+                        const uint32_t B = totk_k;
+                        const uint32_t r16 = (uint32_t)(dbase & 15);
+                        const uint64_t room = P.data_cap[k] > dbase ? P.data_cap[k] - dbase : 0;
+                        const uint32_t hi_ok = r16 + (uint32_t)(B < room ? B : room);  // shifted local end of writable bytes
+                        uint8_t* gbase = P.out_data[k] + (dbase - r16);
+                        for (uint32_t c0 = 0; c0 < r16 + B; c0 += CH) {
+                            for (uint32_t j = tid; j < tile_rows; j += THREADS) {
+                                const uint32_t f = wl[j], len = f >> 16;
+                                const uint32_t st = ost[osh + j] - (uint32_t)dbase + r16;  // shifted tile-local start
+                                const uint32_t lo = st > c0 ? st : c0, hi = st + len < c0 + CH ? st + len : c0 + CH;
+                                const uint8_t* sp = sm.data + PRE + (f & 0xffffu) - st;
+                                for (uint32_t x = lo; x < hi; x++) stage[x - c0] = sp[x];  // (word-wise copies measured slower)
+                            }
+                            __syncthreads();
+                            const uint32_t cend = c0 + CH < r16 + B ? c0 + CH : r16 + B;
+                            for (uint32_t x0 = c0 + tid * 16; x0 < cend; x0 += THREADS * 16)
+                                if (x0 >= r16 && x0 + 16 <= hi_ok) *reinterpret_cast<uint4*>(gbase + x0) = *reinterpret_cast<const uint4*>(stage + (x0 - c0));
+                            // the (at most two) partial vectors at the column's first and last byte: one byte per lane
+                            if (tid < 32) {
+                                const uint32_t tv0 = hi_ok & ~15u;
+                                const uint32_t x = tid < 16 ? (uint32_t)tid : tv0 + (uint32_t)(tid - 16);
+                                const bool head = tid < 16 && c0 == 0 && r16 != 0;
+                                const bool tail = tid >= 16 && (hi_ok & 15u) != 0 && tv0 >= c0 && tv0 < cend && !(tv0 == 0 && r16 != 0);
+                                if ((head || tail) && x >= r16 && x < hi_ok) gbase[x] = stage[x - c0];
+                            }
+                            __syncthreads();
+                        }
+                        __syncthreads();
+                    }
+                }
+            } else if (nrow != 0) {
+                uint64_t off[KMAX];
+#pragma unroll
+                for (int k = 0; k < KMAX; k++) off[k] = k < (EXACT ? KMAX : P.nsel) ? sm.tile_prefix[2 + k] + exk[k] : 0;
+                uint32_t rec_local = 0;
+                auto emit = [&](const Rec<KMAX>& r, uint64_t start_abs) {
+                    if (r.err != K_OK || (HP && !eval_pred(P.pred, r.eq))) { rec_local++; return; }
+                    if (row == 0) P.result->first_row_ordinal = rec0 + rec_local;
+                    const bool row_ok = row < P.row_cap;
+                    if (r.slow) {
+                        uint64_t dst_off[MAXSEL];
+                        uint32_t maxlen[MAXSEL];
+                        SlowOut so;
+#pragma unroll
+                        for (int k = 0; k < KMAX; k++) { dst_off[k] = off[k]; maxlen[k] = r.f[k]; }
+                        slow_record(P, src, start_abs, true, dst_off, maxlen, &so);
+                    }
+#pragma unroll
+                    for (int k = 0; k < KMAX; k++) {
+                        if (k < (EXACT ? KMAX : P.nsel)) {
+                            uint32_t len = r.slow ? r.f[k] : (r.f[k] >> 16);
+                            if (row_ok) P.out_off[k][row] = (uint32_t)off[k];
+                            if (!r.slow && off[k] + len <= P.data_cap[k]) {
+                                const uint8_t* s = sm.data + PRE + (r.f[k] & 0xffffu);
+                                uint8_t* d = P.out_data[k] + off[k];
+                                for (uint32_t i = 0; i < len; i++) d[i] = s[i];
+                            }
+                            off[k] += len;
+                        }
+                    }
+                    row++; rec_local++;
+                };
+                if (flat_ok) {
+                    for (int q = 0; q < L; q++) {
+                        const int i = i0 + tid * L + q;
+                        if (i > m_last_v) break;
+                        Rec<KMAX> r;
+                        if (flat_line<KMAX, EXACT, HP>(P, sm, src, lits, lits_in_smem, tile_base, i, nterm, rel_n, rel_ds, hasq, r))
+                            emit(r, tile_base + (i == 0 ? 0 : (uint64_t)sm.sidx[sm.ord[i - 1]] + 1));
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < WPT; j++) {
+                        uint32_t m = rs[j];
+                        while (m) {
+                            int b = __ffs(m) - 1; m &= m - 1;
+                            const int ws = (tid * WPT + j) * 32 + b;
+                            Rec<KMAX> r;
+                            if (generic_record<KMAX, EXACT, HP>(P, sm, src, tile_base, ws, rel_n, r)) emit(r, tile_base + ws);
+                        }
+                    }
+                }
+            }
+        }
         __syncthreads();  // smem is reused by the next tile
     }
 }
