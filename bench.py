@@ -309,6 +309,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batches", type=int, default=16)
     ap.add_argument("--e2e-workers", type=int, default=4)
+    ap.add_argument("--e2e-sweep", default="", help="e.g. 8x4,16x8: time these (batches x workers) settings of the e2e leg, report the best")
     args = ap.parse_args()
     ORD_ROWS, CUST_ROWS, PROD_ROWS, PEOPLE_ROWS, INDEX_ROWS = args.orders, args.customers, args.products, args.people, args.index_rows
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -550,167 +551,188 @@ def main():
         # cpb_memcpy_h2d), so the H2D engine never idles; the main context parses / indexes the build sides as they
         # arrive; --e2e-workers contexts (one CUDA stream each) parse, join and serialise the probe batches and copy the
         # CSV text back (cpb_table_to_csv_into) — D2H runs on the other DMA engine, concurrently with the uploads.
-        nbatch = max(2, args.e2e_batches)
-        oview = h_orders.array()
-        bounds = [0]
-        for b in range(1, nbatch):
-            pos = b * h_orders.nbytes // nbatch
-            nl = int(np.flatnonzero(oview[pos:pos + 4096] == 10)[0])  # synthetic rows hold no quoted newlines
-            bounds.append(pos + nl + 1)
-        bounds.append(h_orders.nbytes)
-        # sink buffer: the README's six output columns as CSV; sized from one probe batch (+ 10 %)
-        t0, _ = cp.parse_csv(ctx, h_orders.ptr, nbytes=bounds[1], spec=ORDER_COLS)
-        tc0, _ = cp.parse_csv(ctx, d_cust, spec=CUST_COLS)
-        tp0, _ = cp.parse_csv(ctx, d_prod, spec=PROD_COLS)
-        per_row = 0  # mean output bytes per joined row: the six sink columns + separators
-        for tab, cols in ((t0, ("qty", "ts")), (tc0, ("name", "surname")), (tp0, ("product", "price"))):
-            for c in cols:
-                nb = C_u64()
-                ctx.lib.cpb_table_col_bytes(ctx.h, tab.h, tab.columns.index(c), 0, len(tab), nb.ref())
-                per_row += nb.value / max(1, len(tab)) + 1
-        del t0, tc0, tp0
-        out_cap = int(ORD_ROWS * per_row * 1.05) + (1 << 20)
-        h_out = ctx.host_alloc(out_cap)
-        out_slots = [(b * (out_cap // nbatch)) & ~15 for b in range(nbatch)] + [out_cap]
-        nwork = max(1, args.e2e_workers)
-        workers = [cp.Context(local) for _ in range(nwork)]
-        wstreams = [torch.cuda.ExternalStream(w.stream, device=torch.device("cuda", local)) for w in workers]
-        ORDER_ASSUME = [("cust_id", 1), ("prod_id", 2), ("qty", 3), ("ts", 4)]
-        out_bytes = [0]
+        def e2e_config(nbatch, nwork):
+            nbatch = max(2, nbatch)
+            oview = h_orders.array()
+            bounds = [0]
+            for b in range(1, nbatch):
+                pos = b * h_orders.nbytes // nbatch
+                nl = int(np.flatnonzero(oview[pos:pos + 4096] == 10)[0])  # synthetic rows hold no quoted newlines
+                bounds.append(pos + nl + 1)
+            bounds.append(h_orders.nbytes)
+            # sink buffer: the README's six output columns as CSV; sized from one probe batch (+ 10 %)
+            t0, _ = cp.parse_csv(ctx, h_orders.ptr, nbytes=bounds[1], spec=ORDER_COLS)
+            tc0, _ = cp.parse_csv(ctx, d_cust, spec=CUST_COLS)
+            tp0, _ = cp.parse_csv(ctx, d_prod, spec=PROD_COLS)
+            per_row = 0  # mean output bytes per joined row: the six sink columns + separators
+            for tab, cols in ((t0, ("qty", "ts")), (tc0, ("name", "surname")), (tp0, ("product", "price"))):
+                for c in cols:
+                    nb = C_u64()
+                    ctx.lib.cpb_table_col_bytes(ctx.h, tab.h, tab.columns.index(c), 0, len(tab), nb.ref())
+                    per_row += nb.value / max(1, len(tab)) + 1
+            del t0, tc0, tp0
+            out_cap = int(ORD_ROWS * per_row * 1.05) + (1 << 20)
+            h_out = ctx.host_alloc(out_cap)
+            out_slots = [(b * (out_cap // nbatch)) & ~15 for b in range(nbatch)] + [out_cap]
+            nwork = max(1, nwork)
+            workers = [cp.Context(local) for _ in range(nwork)]
+            wstreams = [torch.cuda.ExternalStream(w.stream, device=torch.device("cuda", local)) for w in workers]
+            ORDER_ASSUME = [("cust_id", 1), ("prod_id", 2), ("qty", 3), ("ts", 4)]
+            out_bytes = [0]
 
-        # device staging the uploader fills (allocated once, like the pinned buffers): build sides + one 16-byte aligned
-        # slot per probe batch
-        up = cp.Context(local)
-        dv_cust, dv_prod = up.device_alloc(h_cust.nbytes), up.device_alloc(h_prod.nbytes)
-        dv_off = [0]
-        for b in range(nbatch):
-            dv_off.append((dv_off[-1] + (bounds[b + 1] - bounds[b]) + 255) & ~255)
-        dv_orders = up.device_alloc(dv_off[-1] + 256)
-        up.sync()
+            # device staging the uploader fills (allocated once, like the pinned buffers): build sides + one 16-byte aligned
+            # slot per probe batch
+            up = cp.Context(local)
+            dv_cust, dv_prod = up.device_alloc(h_cust.nbytes), up.device_alloc(h_prod.nbytes)
+            dv_off = [0]
+            for b in range(nbatch):
+                dv_off.append((dv_off[-1] + (bounds[b + 1] - bounds[b]) + 255) & ~255)
+            dv_orders = up.device_alloc(dv_off[-1] + 256)
+            up.sync()
 
-        def join_e2e():
-            t_a = time.perf_counter()
-            written = [0] * nbatch
-            rows_out = [0] * nbatch
-            ready = threading.Event()
-            got_prod, got_cust = threading.Event(), threading.Event()
-            got = [threading.Event() for _ in range(nbatch)]
-            box = {}
-            errs = []
-            tmarks = {}
+            DEBUG = bool(os.environ.get("BENCH_DEBUG"))
 
-            def fail(ex):
-                errs.append(ex)
-                for ev in [ready, got_prod, got_cust] + got:
-                    ev.set()
+            def join_e2e():
+                t_a = time.perf_counter()
+                written = [0] * nbatch
+                rows_out = [0] * nbatch
+                ready = threading.Event()
+                got_prod, got_cust = threading.Event(), threading.Event()
+                got = [threading.Event() for _ in range(nbatch)]
+                box = {}
+                errs = []
+                tmarks = {}
 
-            def upload():  # one thread keeps the H2D engine busy from the first byte to the last
+                def fail(ex):
+                    errs.append(ex)
+                    for ev in [ready, got_prod, got_cust] + got:
+                        ev.set()
+
+                def upload():  # one thread keeps the H2D engine busy from the first byte to the last
+                    try:
+                        up.lib.cpb_memcpy_h2d(up.h, dv_prod.ptr, h_prod.ptr, h_prod.nbytes); got_prod.set()
+                        up.lib.cpb_memcpy_h2d(up.h, dv_cust.ptr, h_cust.ptr, h_cust.nbytes); got_cust.set()
+                        for b in range(nbatch):
+                            up.lib.cpb_memcpy_h2d(up.h, dv_orders.ptr + dv_off[b], h_orders.ptr + bounds[b], bounds[b + 1] - bounds[b])
+                            got[b].set()
+                        tmarks["upload_done"] = time.perf_counter() - t_a
+                    except Exception as ex:
+                        fail(ex)
+
+                def work(wi):
+                    try:
+                        w = workers[wi]
+                        for b in range(wi, nbatch, nwork):
+                            got[b].wait()
+                            nb = bounds[b + 1] - bounds[b]
+                            if b == 0:
+                                t, e = cp.parse_csv(w, dv_orders.ptr + dv_off[b], on_device=True, nbytes=nb, spec=ORDER_COLS)
+                            else:
+                                t, e = cp.parse_csv(w, dv_orders.ptr + dv_off[b], on_device=True, nbytes=nb, spec=ORDER_ASSUME,
+                                                    header_from_first_row=False, num_fields=5)
+                            assert e is None
+                            ready.wait()  # the build sides are parsed / indexed concurrently on the main context
+                            if errs:
+                                return
+                            w0 = time.perf_counter()
+                            j = t.join(box["cidx"], "cust_id").join(box["pidx"])
+                            rows_out[b] = len(j)
+                            if DEBUG:  # (the split join / sink timing needs a sync the pipeline itself does not)
+                                w.sync()
+                            w1 = time.perf_counter()
+                            written[b] = j.to_csv_into(h_out, out_slots[b], *SINK_COLS, header=(b == 0))
+                            w2 = time.perf_counter()
+                            tmarks.setdefault("join_ms", []).append((w1 - w0) * 1e3); tmarks.setdefault("sink_ms", []).append((w2 - w1) * 1e3)
+                            assert out_slots[b] + written[b] <= out_slots[b + 1]
+                            del j, t
+                        tmarks["worker%d_done" % wi] = time.perf_counter() - t_a
+                    except Exception as ex:  # surfaced by the main thread
+                        fail(ex)
+                th = [threading.Thread(target=upload)] + [threading.Thread(target=work, args=(i,)) for i in range(nwork)]
+                for t in th:
+                    t.start()
                 try:
-                    up.lib.cpb_memcpy_h2d(up.h, dv_prod.ptr, h_prod.ptr, h_prod.nbytes); got_prod.set()
-                    up.lib.cpb_memcpy_h2d(up.h, dv_cust.ptr, h_cust.ptr, h_cust.nbytes); got_cust.set()
-                    for b in range(nbatch):
-                        up.lib.cpb_memcpy_h2d(up.h, dv_orders.ptr + dv_off[b], h_orders.ptr + bounds[b], bounds[b + 1] - bounds[b])
-                        got[b].set()
-                    tmarks["upload_done"] = time.perf_counter() - t_a
+                    got_prod.wait()
+                    tp, err = cp.parse_csv(ctx, dv_prod, spec=PROD_COLS)
+                    assert err is None
+                    pidx = tp.index_on("prod_id", unique=True)
+                    got_cust.wait()
+                    tc, err = cp.parse_csv(ctx, dv_cust, spec=CUST_COLS)
+                    assert err is None
+                    if world > 1:
+                        tc = allgather_table_nccl(ctx, tc)
+                    cidx = tc.index_on("id", unique=True)
+                    warm, _ = cp.parse_csv(ctx, b"cust_id,prod_id\n0,0\n")
+                    warm.join(cidx, "cust_id").join(pidx)  # builds the probe tables once, before the workers share the indices
+                    ctx.sync()
+                    box["cidx"], box["pidx"] = cidx, pidx
+                    ready.set()
                 except Exception as ex:
                     fail(ex)
+                t_b = time.perf_counter()
+                for t in th:
+                    t.join()
+                if errs:
+                    raise errs[0]
+                out_bytes[0] = sum(written)
+                if DEBUG:
+                    print("e2e step: build %.1f ms, probe+sink tail %.1f ms; upload done %.1f, workers done %.1f / %.1f; per batch join %.1f sink %.1f ms"
+                          % ((t_b - t_a) * 1e3, (time.perf_counter() - t_b) * 1e3, tmarks.get("upload_done", 0) * 1e3, min(v for k, v in tmarks.items() if k.startswith("worker")) * 1e3,
+                             max(v for k, v in tmarks.items() if k.startswith("worker")) * 1e3, sum(tmarks.get("join_ms", [0])) / max(1, len(tmarks.get("join_ms", [0]))),
+                             sum(tmarks.get("sink_ms", [0])) / max(1, len(tmarks.get("sink_ms", [0])))), file=sys.stderr)
+                return sum(rows_out)
 
-            def work(wi):
-                try:
-                    w = workers[wi]
-                    for b in range(wi, nbatch, nwork):
-                        got[b].wait()
-                        nb = bounds[b + 1] - bounds[b]
-                        if b == 0:
-                            t, e = cp.parse_csv(w, dv_orders.ptr + dv_off[b], on_device=True, nbytes=nb, spec=ORDER_COLS)
-                        else:
-                            t, e = cp.parse_csv(w, dv_orders.ptr + dv_off[b], on_device=True, nbytes=nb, spec=ORDER_ASSUME,
-                                                header_from_first_row=False, num_fields=5)
-                        assert e is None
-                        ready.wait()  # the build sides are parsed / indexed concurrently on the main context
-                        if errs:
-                            return
-                        w0 = time.perf_counter()
-                        j = t.join(box["cidx"], "cust_id").join(box["pidx"])
-                        rows_out[b] = len(j)
-                        w.sync(); w1 = time.perf_counter()
-                        written[b] = j.to_csv_into(h_out, out_slots[b], *SINK_COLS, header=(b == 0))
-                        w2 = time.perf_counter()
-                        tmarks.setdefault("join_ms", []).append((w1 - w0) * 1e3); tmarks.setdefault("sink_ms", []).append((w2 - w1) * 1e3)
-                        assert out_slots[b] + written[b] <= out_slots[b + 1]
-                        del j, t
-                    tmarks["worker%d_done" % wi] = time.perf_counter() - t_a
-                except Exception as ex:  # surfaced by the main thread
-                    fail(ex)
-            th = [threading.Thread(target=upload)] + [threading.Thread(target=work, args=(i,)) for i in range(nwork)]
-            for t in th:
-                t.start()
-            try:
-                got_prod.wait()
-                tp, err = cp.parse_csv(ctx, dv_prod, spec=PROD_COLS)
-                assert err is None
-                pidx = tp.index_on("prod_id", unique=True)
-                got_cust.wait()
-                tc, err = cp.parse_csv(ctx, dv_cust, spec=CUST_COLS)
-                assert err is None
+            def timed_multi(fn, steps, warmup):
+                for _ in range(warmup):
+                    fn()
+                for w in [ctx] + workers:
+                    w.sync()
+                torch.cuda.synchronize()
                 if world > 1:
-                    tc = allgather_table_nccl(ctx, tc)
-                cidx = tc.index_on("id", unique=True)
-                warm, _ = cp.parse_csv(ctx, b"cust_id,prod_id\n0,0\n")
-                warm.join(cidx, "cust_id").join(pidx)  # builds the probe tables once, before the workers share the indices
-                ctx.sync()
-                box["cidx"], box["pidx"] = cidx, pidx
-                ready.set()
-            except Exception as ex:
-                fail(ex)
-            t_b = time.perf_counter()
-            for t in th:
-                t.join()
-            if errs:
-                raise errs[0]
-            out_bytes[0] = sum(written)
-            if os.environ.get("BENCH_DEBUG"):
-                print("e2e step: build %.1f ms, probe+sink tail %.1f ms; upload done %.1f, workers done %.1f / %.1f; per batch join %.1f sink %.1f ms"
-                      % ((t_b - t_a) * 1e3, (time.perf_counter() - t_b) * 1e3, tmarks.get("upload_done", 0) * 1e3, min(v for k, v in tmarks.items() if k.startswith("worker")) * 1e3,
-                         max(v for k, v in tmarks.items() if k.startswith("worker")) * 1e3, sum(tmarks.get("join_ms", [0])) / max(1, len(tmarks.get("join_ms", [0]))),
-                         sum(tmarks.get("sink_ms", [0])) / max(1, len(tmarks.get("sink_ms", [0])))), file=sys.stderr)
-            return sum(rows_out)
+                    dist.barrier()
+                e0 = torch.cuda.Event(enable_timing=True)
+                ends = [torch.cuda.Event(enable_timing=True) for _ in range(1 + len(wstreams))]
+                e0.record(stream)
+                rows = 0
+                for _ in range(steps):
+                    rows = fn()
+                ends[0].record(stream)
+                for e, ws in zip(ends[1:], wstreams):
+                    e.record(ws)
+                for w in [ctx] + workers:
+                    w.sync()
+                torch.cuda.synchronize()
+                ms = max(e0.elapsed_time(e) for e in ends)
+                if world > 1:
+                    dist.barrier()
+                    tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+                    ms = float(tms.item())
+                return ms / steps, rows
 
-        def timed_multi(fn, steps, warmup):
-            for _ in range(warmup):
-                fn()
-            for w in [ctx] + workers:
+            ms, rows = timed_multi(join_e2e, args.steps, args.warmup)
+            first = bytes(h_out.array()[:64])
+            for w in workers + [up]:
                 w.sync()
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            e0 = torch.cuda.Event(enable_timing=True)
-            ends = [torch.cuda.Event(enable_timing=True) for _ in range(1 + len(wstreams))]
-            e0.record(stream)
-            rows = 0
-            for _ in range(steps):
-                rows = fn()
-            ends[0].record(stream)
-            for e, ws in zip(ends[1:], wstreams):
-                e.record(ws)
-            for w in [ctx] + workers:
-                w.sync()
-            torch.cuda.synchronize()
-            ms = max(e0.elapsed_time(e) for e in ends)
-            if world > 1:
-                dist.barrier()
-                tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-                ms = float(tms.item())
-            return ms / steps, rows
+            return ms, rows, out_bytes[0], first, nbatch, nwork
 
-        ms_e2e, e2e_rows = timed_multi(join_e2e, args.steps, args.warmup)
+        # --e2e-sweep "8x4,16x8": time several (batches x workers) settings, report the best one (stderr lists them all)
+        configs = [(args.e2e_batches, args.e2e_workers)]
+        if args.e2e_sweep:
+            configs = [tuple(int(x) for x in c.split("x")) for c in args.e2e_sweep.split(",")]
+        best = None
+        for nb_, nw_ in configs:
+            r = e2e_config(nb_, nw_)
+            if rank == 0 and len(configs) > 1:
+                print("e2e sweep: batches %d workers %d -> %.1f ms/step" % (r[4], r[5], r[0]), file=sys.stderr)
+            if best is None or r[0] < best[0]:
+                best = r
+        ms_e2e, e2e_rows, out_bytes_best, first, nbatch, nwork = best
         assert e2e_rows == out_rows, (e2e_rows, out_rows)
         # the sink really holds the result: header + one line per joined row
-        first = bytes(h_out.array()[:64])
         assert first.startswith(b"name,surname,qty,product,price,ts\n"), first
         e2e = {"value": world * ORD_ROWS / (ms_e2e * 1e-3), "unit": "rows/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": h_cust.nbytes + h_prod.nbytes + h_orders.nbytes, "d2h_bytes_per_step": out_bytes[0],
+               "h2d_bytes_per_step": h_cust.nbytes + h_prod.nbytes + h_orders.nbytes, "d2h_bytes_per_step": out_bytes_best,
                "batches": nbatch, "workers": nwork, "host_numa_node": numa_node, "sink": "ToCsv(%s)" % ",".join(SINK_COLS),
                "note": "pinned host CSV -> H2D (one uploader, cpb_memcpy_h2d) -> parse/index/join/join/ToCsv on the GPU through the "
                        "public API -> D2H of the CSV text of every joined row into pinned host memory; the probe file is streamed "

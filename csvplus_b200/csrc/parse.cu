@@ -139,12 +139,27 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
         o.delimiter = sub.delimiter; o.comment = sub.comment;
         if (sub.buffer) { in = sub.buffer->as<uint8_t>(); n = sub.nbytes; }
     }
-    const SubTable* subs_dev = sub.table ? sub.table->as<SubTable>() : nullptr;
+    const SubTable* subs_dev = sub.table ? sub.table->as<SubTable>() : nullptr;  // (reset below when no stand-in byte is in play)
     // CommentChar / LazyQuotes / TrimLeadingSpace change what "inside quotes" means: they take the general
     // (DFA-composition, multi-pass) path of parse_general.cu; the default options take the single-pass scan.
-    const bool general = o.comment != 0 || o.lazy_quotes || o.trim_leading_space;
+    const bool special = o.comment != 0 || o.lazy_quotes || o.trim_leading_space;
+    // ... unless the input lets the single-pass scan stand in for it (the common case: no stand-in bytes in play, a
+    // delimiter TrimLeadingSpace would not eat).  The scan then runs *optimistically*:
+    //   * TrimLeadingSpace is exact in it: leading white space of a quote-free line's fields is skipped where the field
+    //     extents are computed, lines with quotes take the options-aware sequential machine (seq_parse_record_gen);
+    //   * CommentChar: a line whose first byte is the comment byte is not a record; if such a line holds a quote (which the
+    //     quote-parity chain has counted) the kernel says so and the parse is redone on the general path;
+    //   * LazyQuotes only ever turns ErrBareQuote / ErrQuote of the strict rules into data: the strict scan runs, and only
+    //     if its first error is one of those two is the parse redone on the general path.
+    // CPB_GENERAL_PATH=dfa forces the general path (tests / timing).
+    bool any_standin = false;
+    for (int i = 0; i < 8; i++) any_standin = any_standin || sub.host_table.bits[i] != 0;
+    const bool delim_is_space = o.delimiter == ' ' || o.delimiter == '\t' || o.delimiter == '\v' || o.delimiter == '\f';
+    static const bool force_dfa = getenv("CPB_GENERAL_PATH") != nullptr && !strcmp(getenv("CPB_GENERAL_PATH"), "dfa");
+    const bool optimistic = special && !sh && !any_standin && !sub.buffer && !(o.trim_leading_space && delim_is_space) && !force_dfa;
+    bool general = special && !optimistic;
     if (sh) {  // a byte-range shard of one file (cpb_parse_csv_shard)
-        if (general || sub.table) throw ArgError{CPB_ERR_UNSUPPORTED, "byte-range shards take the default reader options only"};
+        if (special || sub.table) throw ArgError{CPB_ERR_UNSUPPORTED, "byte-range shards take the default reader options only"};
         if (sh->index > 0 && (o.header_from_first_row || o.num_fields == 0))
             throw ArgError{CPB_ERR_ARG, "shards after the first need the resolved header (name -> index) and an explicit field count"};
         if (sh->own_bytes > n) throw ArgError{CPB_ERR_ARG, "own_bytes exceeds the buffer"};
@@ -153,8 +168,14 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
 
     // ---- header kernel (first record + sampling)
     Buf hbuf = dev_alloc(c, sizeof(HeaderOut));
-    if (general) general_header(c, in, n, o, &sub, hbuf->as<HeaderOut>());
-    else {
+    if (special) {
+        general_header(c, in, n, o, &sub, hbuf->as<HeaderOut>());
+        if (optimistic) {  // the capacity estimate of the single-pass scan needs the newline / field-length samples too
+            KernelTimer kt(c, "csv_header", 0);
+            csv_header_kernel<<<1, 256, 0, c->stream>>>(in, n, (int)o.delimiter, nullptr, hbuf->as<HeaderOut>(), 1);
+            CPB_CUDA(cudaGetLastError());
+        }
+    } else {
         KernelTimer kt(c, "csv_header", 0);
         csv_header_kernel<<<1, 256, 0, c->stream>>>(in, n, (int)o.delimiter, subs_dev, hbuf->as<HeaderOut>());
         CPB_CUDA(cudaGetLastError());
@@ -306,7 +327,9 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
             if (P.ntiles) P.ntiles = (uint32_t)std::min<uint64_t>(P.ntiles, sh->own_bytes / TILE + 1);
         }
     }
-    P.subs = subs_dev;
+    P.subs = optimistic ? nullptr : subs_dev;
+    P.trim = optimistic && o.trim_leading_space ? 1u : 0u;
+    P.comment = optimistic ? o.comment : 0u;
 
     if (P.ntiles == 0) { if (sh && sh->records) *sh->records = 0; return empty_table(names); }
 
@@ -316,8 +339,9 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
     P.lits = lits->as<uint8_t>();
     P.lits_len = (uint32_t)comp.lits.size();
 
-    if (general) {
+    auto run_general = [&]() -> std::shared_ptr<Table> {
         GenResult gr;
+        P.subs = subs_dev; P.trim = 0; P.comment = 0;
         general_parse(c, P, o, &sub, data_start, &gr);
         auto t = std::make_shared<Table>();
         t->ctx = c; t->nrows = (int64_t)gr.rows; t->first_line = line_base;
@@ -335,7 +359,8 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
             t->cols.push_back(col);
         }
         return t;
-    }
+    };
+    if (general) return run_general();
 
     // ---- capacities (exact totals always come back; overflow => one exact rerun)
     const int NP = 2 + nsel;
@@ -380,6 +405,11 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
         CPB_CUDA(cudaMemsetAsync(&P.result->err_key, 0xff, 24, c->stream));
         CPB_CUDA(cudaMemsetAsync(P.words, 0, (size_t)P.ntiles * (NP * 8 + 4), c->stream));
         uint64_t algo = n;  // S_in; S_out added by the caller of stats from the totals
+        if (P.trim || P.comment) {  // optimistic TrimLeadingSpace / CommentChar: the guarded instantiations carry the extra checks
+            if (nsel <= 4) launch_scan<4, false>(c, P, algo);
+            else if (nsel <= 8) launch_scan<8, false>(c, P, algo);
+            else launch_scan<16, false>(c, P, algo);
+        } else
         switch (sh ? 99 : nsel) {  // kernels specialised on the exact number of extracted columns (no per-column guards); shards: the guarded one
             case 1: launch_scan<1, true>(c, P, algo); break;
             case 2: launch_scan<2, true>(c, P, algo); break;
@@ -395,6 +425,14 @@ std::shared_ptr<Table> parse_csv(Ctx* c, const uint8_t* in_arg, uint64_t n_arg, 
         CPB_CUDA(cudaMemcpyAsync(hr, P.result, sizeof(ParseResult), cudaMemcpyDeviceToHost, c->stream));
         sync_stream(c);
         res = *hr;
+        if (optimistic) {  // did the shortcut hold?
+            const int ekind = res.err_key == ~0ull ? 0 : (int)((res.err_key >> 8) & 0xff);
+            const bool lazy_matters = o.lazy_quotes && (ekind == CPB_E_BARE_QUOTE || ekind == CPB_E_QUOTE);
+            if (res.need_general || lazy_matters) {
+                offs.clear(); datas.clear();
+                return run_general();
+            }
+        }
         bool overflow = res.totals[1] > row_cap;
         for (int k = 0; k < nsel; k++) {
             if (res.totals[2 + k] > 0xffffffffull)

@@ -117,81 +117,6 @@ __global__ void g_starts(const uint8_t* __restrict__ in, uint64_t n, GenOpts o, 
     if (!WRITE) counts[c] = k;
 }
 
-// Exact sequential restatement of encoding/csv readRecord with LazyQuotes / TrimLeadingSpace (single-byte comma).
-template <class Sink>
-__device__ SeqResult seq_parse_record_gen(const ByteSrc& src, uint64_t start, int delim, bool lazy, bool trim, const uint32_t* sp_bits, Sink& sink) {
-    uint64_t pos = start;
-    int f = 0;
-    auto is_sp = [&](int c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r' || sub_is(sp_bits, c); };
-    for (;;) {  // parseField
-        sink.begin_field(f);
-        if (trim) {
-            // bytes.IndexFunc(line, !unicode.IsSpace): the line's own "\n" is white space too, so a field of
-            // spaces up to the end of the line is empty and ends the record
-            for (;;) {
-                int c = src.get(pos);
-                if (c == '\n') { sink.end_field(); return {K_OK, f + 1, pos + 1}; }
-                if (c < 0) { sink.end_field(); return {K_OK, f + 1, src.n}; }
-                if (!is_sp(c)) break;
-                pos++;
-            }
-        }
-        int c = src.get(pos);
-        if (c != '"') {
-            uint64_t fb = pos;
-            for (;;) {
-                c = src.get(pos);
-                if (c == delim) { sink.end_field(); pos++; f++; break; }
-                if (c == '\n' || c < 0) {
-                    if (pos > fb && src.get(pos - 1) == '\r') sink.unput();
-                    sink.end_field();
-                    return {K_OK, f + 1, c < 0 ? src.n : pos + 1};
-                }
-                if (c == '"' && !lazy) return {K_BARE, f + 1, pos};
-                sink.put(c);
-                pos++;
-            }
-        } else {
-            pos++;
-            for (;;) {
-                c = src.get(pos);
-                if (c < 0) {  // abrupt end of file inside quotes
-                    if (!lazy) return {K_QUOTE, f + 1, pos};
-                    sink.end_field();
-                    return {K_OK, f + 1, src.n};
-                }
-                if (c == '"') {
-                    int c2 = src.get(pos + 1);
-                    if (c2 == '"') { sink.put('"'); pos += 2; continue; }
-                    if (c2 == delim) { sink.end_field(); pos += 2; f++; break; }
-                    if (c2 == '\n') { sink.end_field(); return {K_OK, f + 1, pos + 2}; }
-                    if (c2 < 0) { sink.end_field(); return {K_OK, f + 1, src.n}; }
-                    if (c2 == '\r') {
-                        int c3 = src.get(pos + 2);
-                        if (c3 == '\n') { sink.end_field(); return {K_OK, f + 1, pos + 3}; }
-                        if (c3 < 0) { sink.end_field(); return {K_OK, f + 1, src.n}; }
-                    }
-                    if (!lazy) return {K_QUOTE, f + 1, pos};
-                    sink.put('"');  // `"` sequence (bare quote) under LazyQuotes
-                    pos++;
-                    continue;
-                }
-                if (c == '\r') {
-                    int c2 = src.get(pos + 1);
-                    if (c2 == '\n') { sink.put('\n'); pos += 2; continue; }
-                    if (c2 < 0) {  // trailing \r before EOF is dropped, then EOF inside quotes
-                        if (!lazy) return {K_QUOTE, f + 1, pos};
-                        sink.end_field();
-                        return {K_OK, f + 1, src.n};
-                    }
-                }
-                sink.put(c);
-                pos++;
-            }
-        }
-    }
-}
-
 struct GenRec { uint32_t lazy, trim; };
 
 // first record (header row / field-count seed), honouring comment and empty lines

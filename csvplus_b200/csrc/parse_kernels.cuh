@@ -75,6 +75,8 @@ struct ParseResult {  // device -> host
     unsigned long long first_row_ordinal;  // record ordinal of output row 0 (~0 if no rows)
     uint32_t fallback_tiles;      // tiles that took the dense fallback
     uint32_t eof_hit;             // a record of this shard was closed by the end of the buffer, not by a terminator
+    uint32_t need_general;        // a comment line that may hold a quote was seen: the quote-parity shortcut does not hold, rerun on the general path
+    uint32_t pad_;
 };
 
 struct ParseParams {
@@ -107,6 +109,9 @@ struct ParseParams {
     uint32_t l2_ahead;     // 1: prefetch the tile one grid-width ahead into L2
     uint32_t ds_is_start;  // data_start is itself the first byte of a record (after a header row); 0 for shards after the first
     uint64_t own_end;
+    // reader options csv_scan_kernel's guarded instantiations take optimistically (parse.cu): TrimLeadingSpace, and the
+    // CommentChar byte (0: none).  The kernels specialised on the column count never read them.
+    uint32_t trim, comment;
 };
 
 // ------------------------------------------------------------------ byte source: staged window or HBM
@@ -178,6 +183,85 @@ __device__ SeqResult seq_parse_record(const ByteSrc& src, uint64_t start, int de
     }
 }
 
+// Exact sequential restatement of encoding/csv readRecord with LazyQuotes / TrimLeadingSpace (single-byte comma).
+template <class Sink>
+__device__ SeqResult seq_parse_record_gen(const ByteSrc& src, uint64_t start, int delim, bool lazy, bool trim, const uint32_t* sp_bits, Sink& sink) {
+    uint64_t pos = start;
+    int f = 0;
+    auto is_sp = [&](int c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r' || sub_is(sp_bits, c); };
+    for (;;) {  // parseField
+        sink.begin_field(f);
+        if (trim) {
+            // bytes.IndexFunc(line, !unicode.IsSpace): the line's own "\n" is white space too, so a field of
+            // spaces up to the end of the line is empty and ends the record
+            for (;;) {
+                int c = src.get(pos);
+                if (c == '\n') { sink.end_field(); return {K_OK, f + 1, pos + 1}; }
+                if (c < 0) { sink.end_field(); return {K_OK, f + 1, src.n}; }
+                if (!is_sp(c)) break;
+                pos++;
+            }
+        }
+        int c = src.get(pos);
+        if (c != '"') {
+            uint64_t fb = pos;
+            for (;;) {
+                c = src.get(pos);
+                if (c == delim) { sink.end_field(); pos++; f++; break; }
+                if (c == '\n' || c < 0) {
+                    if (pos > fb && src.get(pos - 1) == '\r') sink.unput();
+                    sink.end_field();
+                    return {K_OK, f + 1, c < 0 ? src.n : pos + 1};
+                }
+                if (c == '"' && !lazy) return {K_BARE, f + 1, pos};
+                sink.put(c);
+                pos++;
+            }
+        } else {
+            pos++;
+            for (;;) {
+                c = src.get(pos);
+                if (c < 0) {  // abrupt end of file inside quotes
+                    if (!lazy) return {K_QUOTE, f + 1, pos};
+                    sink.end_field();
+                    return {K_OK, f + 1, src.n};
+                }
+                if (c == '"') {
+                    int c2 = src.get(pos + 1);
+                    if (c2 == '"') { sink.put('"'); pos += 2; continue; }
+                    if (c2 == delim) { sink.end_field(); pos += 2; f++; break; }
+                    if (c2 == '\n') { sink.end_field(); return {K_OK, f + 1, pos + 2}; }
+                    if (c2 < 0) { sink.end_field(); return {K_OK, f + 1, src.n}; }
+                    if (c2 == '\r') {
+                        int c3 = src.get(pos + 2);
+                        if (c3 == '\n') { sink.end_field(); return {K_OK, f + 1, pos + 3}; }
+                        if (c3 < 0) { sink.end_field(); return {K_OK, f + 1, src.n}; }
+                    }
+                    if (!lazy) return {K_QUOTE, f + 1, pos};
+                    sink.put('"');  // `"` sequence (bare quote) under LazyQuotes
+                    pos++;
+                    continue;
+                }
+                if (c == '\r') {
+                    int c2 = src.get(pos + 1);
+                    if (c2 == '\n') { sink.put('\n'); pos += 2; continue; }
+                    if (c2 < 0) {  // trailing \r before EOF is dropped, then EOF inside quotes
+                        if (!lazy) return {K_QUOTE, f + 1, pos};
+                        sink.end_field();
+                        return {K_OK, f + 1, src.n};
+                    }
+                }
+                sink.put(c);
+                pos++;
+            }
+        }
+    }
+}
+
+// the ASCII white space TrimLeadingSpace trims inside a line (unicode.IsSpace minus '\n'; the multi-byte spaces go
+// through stand-in bytes and the general path)
+__device__ __forceinline__ bool is_space_byte(int c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r'; }
+
 // ------------------------------------------------------------------ header kernel
 struct HeaderOut {
     int32_t err;        // K_* of the first record (0 ok)
@@ -206,14 +290,15 @@ struct HeaderSink {
 // Parses the first record (makeHeader's reader.Read(), csvplus.go:1150) and samples newline density
 // in three 64 KiB windows for the row-capacity estimate.  The first 8 KiB are staged in shared memory
 // so that the sequential parse of a normal header never waits on HBM.
-static __global__ void csv_header_kernel(const uint8_t* in, uint64_t n, int delim, const SubTable* subs, HeaderOut* out) {
+// sample_only: the first record was parsed by the options-aware g_header_kernel (parse_general.cu); only the sampling runs.
+static __global__ void csv_header_kernel(const uint8_t* in, uint64_t n, int delim, const SubTable* subs, HeaderOut* out, int sample_only = 0) {
     __shared__ unsigned long long s_nl;
     __shared__ uint8_t s_head[8192];
     const uint64_t staged = n < 8192 ? n : 8192;
     for (uint64_t i = threadIdx.x; i < staged; i += blockDim.x) s_head[i] = in[i];
     if (threadIdx.x == 0) s_nl = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !sample_only) {
         ByteSrc src{in, n, s_head, 0, staged};
         uint64_t pos = 0;
         // skip empty lines: "\n", "\r\n", and a lone trailing "\r" before EOF
@@ -390,8 +475,11 @@ struct SlowSink {
 struct SlowOut { uint32_t ulen[MAXSEL]; uint32_t present, eq; int nf, err; };
 
 // count mode (emit=false): lengths / predicate terms / error of one record; emit mode: store the unescaped values.
-static __device__ __noinline__ void slow_record(const ParseParams& P, const ByteSrc& src, uint64_t start, bool emit,
-                                         const uint64_t* dst_off, const uint32_t* maxlen, SlowOut* o) {
+// (TRIM: the options-aware machine with TrimLeadingSpace — only the guarded kernel instantiations reference it, so the
+// kernels specialised on the column count carry exactly the code they carried before)
+template <bool TRIM>
+static __device__ __noinline__ void slow_record_t(const ParseParams& P, const ByteSrc& src, uint64_t start, bool emit,
+                                                  const uint64_t* dst_off, const uint32_t* maxlen, SlowOut* o) {
     SlowSink sink(P, emit);
     if (emit) {
         for (int k = 0; k < P.nsel; k++) {
@@ -400,11 +488,22 @@ static __device__ __noinline__ void slow_record(const ParseParams& P, const Byte
             sink.maxlen[k] = maxlen[k];
         }
     }
-    SeqResult s = seq_parse_record(src, start, (int)P.delim, sink);
+    SeqResult s;
+    if (TRIM) {
+        const uint32_t no_sp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        s = seq_parse_record_gen(src, start, (int)P.delim, false, true, no_sp, sink);
+    } else s = seq_parse_record(src, start, (int)P.delim, sink);
     o->err = s.err; o->nf = s.nfields; o->present = sink.present; o->eq = sink.eq;
     // (shards: a record closed by the end of the buffer instead of a terminator — benign race, every writer stores 1)
     if (!emit && s.err == K_OK && s.next >= src.n && src.n > 0 && src.get(src.n - 1) != '\n') P.result->eof_hit = 1u;
     for (int k = 0; k < P.nsel; k++) o->ulen[k] = ((sink.present >> k) & 1) ? sink.ulen[k] : 0;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void slow_record(const ParseParams& P, const ByteSrc& src, uint64_t start, bool emit,
+                                            const uint64_t* dst_off, const uint32_t* maxlen, SlowOut* o) {
+    if (!EXACT && P.trim) slow_record_t<true>(P, src, start, emit, dst_off, maxlen, o);
+    else slow_record_t<false>(P, src, start, emit, dst_off, maxlen, o);
 }
 
 template <int KMAX>
@@ -439,7 +538,7 @@ __device__ __forceinline__ void finish_record(const ParseParams& P, Rec<KMAX>& r
 template <int KMAX, bool EXACT>
 __device__ __forceinline__ void run_slow(const ParseParams& P, const ByteSrc& src, uint64_t start_abs, Rec<KMAX>& r) {
     SlowOut so;
-    slow_record(P, src, start_abs, false, nullptr, nullptr, &so);
+    slow_record<EXACT>(P, src, start_abs, false, nullptr, nullptr, &so);
     r.err = so.err; r.nf = so.nf; r.present = so.present; r.eq = so.eq; r.slow = true; r.err_slot = 0;
 #pragma unroll
     for (int k = 0; k < KMAX; k++) r.f[k] = k < (EXACT ? KMAX : P.nsel) ? so.ulen[k] : 0;
@@ -463,6 +562,12 @@ __device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem&
         if (e == start) return false;                          // empty line: not a record
         if (tile_has_q && count_bits(sm.Qb, start, e_nl) != 0) to_slow = true;
     }
+    if (!EXACT && P.comment != 0 && sm.data[PRE + start] == (uint8_t)P.comment) {
+        // a comment line (checked on the raw line, before any trimming): not a record.  Its quotes, if it has any, were
+        // counted by the parity chain though — the parse is then redone on the general path (rare; parse.cu)
+        if (to_slow) P.result->need_general = 1u;
+        return false;
+    }
     if (to_slow) {
         run_slow<KMAX, EXACT>(P, src, tile_base + start, r);
     } else {
@@ -474,8 +579,9 @@ __device__ __forceinline__ bool flat_line(const ParseParams& P, const ParseSmem&
             if (k < (EXACT ? KMAX : P.nsel)) {
                 const int target = P.sel_field[k];
                 if (target < nf) {
-                    const int fb = target == 0 ? start : (int)sm.sidx[a + target] + 1;
+                    int fb = target == 0 ? start : (int)sm.sidx[a + target] + 1;
                     const int fe = target + 1 < nf ? (int)sm.sidx[a + target + 1] : e;
+                    if (!EXACT && P.trim) while (fb < fe && is_space_byte(sm.data[PRE + fb])) fb++;  // TrimLeadingSpace
                     const uint32_t len = (uint32_t)(fe - fb);
                     r.f[k] = (uint32_t)fb | (len << 16);
                     r.present |= 1u << k;
@@ -505,6 +611,7 @@ __device__ __forceinline__ bool generic_record(const ParseParams& P, const Parse
     int c0 = sm.data[PRE + ws];
     if (c0 == '\n') return false;
     if (c0 == '\r' && (sm.data[PRE + ws + 1] == '\n' || ws + 1 >= rel_n)) return false;
+    if (!EXACT && P.comment != 0 && c0 == (int)P.comment) { P.result->need_general = 1u; return false; }  // (dense tiles do not look for its quotes)
     r.present = 0; r.eq = 0; r.err = K_OK; r.err_slot = 0;
     run_slow<KMAX, EXACT>(P, src, tile_base + ws, r);
     finish_record<KMAX, EXACT, HP>(P, r);
@@ -1046,7 +1153,7 @@ __global__ void __launch_bounds__(THREADS, KMAX <= 8 ? 768 / THREADS : 1) csv_sc
                         SlowOut so;
 #pragma unroll
                         for (int k = 0; k < KMAX; k++) { dst_off[k] = off[k]; maxlen[k] = r.f[k]; }
-                        slow_record(P, src, start_abs, true, dst_off, maxlen, &so);
+                        slow_record<EXACT>(P, src, start_abs, true, dst_off, maxlen, &so);
                     }
 #pragma unroll
                     for (int k = 0; k < KMAX; k++) {

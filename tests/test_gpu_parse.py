@@ -253,6 +253,70 @@ def test_general_options_big_and_edges():
             check_parity(data, opts=orc.Opts(**{**o.__dict__, "fields_per_record": -1}), assume={"x": 0, "y": 1})
 
 
+def _route(fn):
+    """runs fn with kernel statistics on; returns (result, True if the general multi-pass path ran)"""
+    ctx = gpu_ctx()
+    ctx.stats(enable=True, reset=True)
+    try:
+        r = fn()
+        st = ctx.stats()
+    finally:
+        ctx.stats(enable=False)
+    assert any(k.startswith("csv_scan") or k.startswith("general") for k in st), st
+    return r, any(k.startswith("general_rec") for k in st)
+
+
+def _clean_with_options(nrows=30000, seed=5, comments=True, spaces=True, crlf=True):
+    """a quote-free file in the people shape with comment lines, leading white space and CRLF sprinkled in"""
+    import random
+    rng = random.Random(seed)
+    out = [b"id,name,surname,born"]
+    for ln in people_csv(nrows, seed).split(b"\n")[1:-1]:
+        if comments and rng.random() < 0.05:
+            out.append(b"#" + rng.choice([b" note", b"", b"x,y,z,w,v", b" , , ,"]))
+        if spaces and rng.random() < 0.5:
+            ln = b",".join(rng.choice([b"", b" ", b"\t", b" \t ", b"\r"]) + f for f in ln.split(b","))
+        out.append(ln + (b"\r" if crlf and rng.random() < 0.3 else b""))
+    return b"\n".join(out) + b"\n"
+
+
+@pytest.mark.parametrize("opts", [dict(comment="#"), dict(trim_leading_space=True), dict(lazy_quotes=True),
+                                  dict(comment="#", trim_leading_space=True, lazy_quotes=True),
+                                  dict(comment="#", trim_leading_space=True, fields_per_record=-1)])
+def test_reader_options_take_the_single_pass_scan_when_the_input_allows(opts):
+    """CommentChar / TrimLeadingSpace / LazyQuotes on input that does not need the general path (no quote inside a comment
+    line, no lazy quote): the fused scan runs, results equal the oracle (csvplus.go:971-993)"""
+    data = _clean_with_options(comments="comment" in opts, spaces=True)
+    o = orc.Opts(**opts)
+    (_, general) = _route(lambda: check_parity(data, opts=o))
+    assert not general
+    (_, general) = _route(lambda: check_parity(data, opts=o, select=["surname", "id"], like={"surname": "Evans"}))
+    assert not general
+    # a few quoted fields (valid under the strict rules, leading white space before the quote when trimming): still one pass
+    q = data.replace(b",Evans,", b', "Ev""ans",' if o.trim_leading_space else b',"Ev""ans",', 40)
+    (_, general) = _route(lambda: check_parity(q, opts=o))
+    assert not general
+
+
+def test_reader_options_fall_back_to_the_general_path_when_they_must():
+    data = _clean_with_options(nrows=20000, comments=True, spaces=False)
+    # a comment line that holds a quote: the parity shortcut does not hold
+    lines = data.split(b"\n")
+    lines.insert(len(lines) // 2, b'# he said "hi')
+    d1 = b"\n".join(lines)
+    (_, general) = _route(lambda: check_parity(d1, opts=orc.Opts(comment="#")))
+    assert general
+    # a lazy quote: strict rules fail on it, LazyQuotes keeps it as data
+    d2 = data.replace(b",Smith,", b',Sm"ith,', 3)
+    (_, general) = _route(lambda: check_parity(d2, opts=orc.Opts(comment="#", lazy_quotes=True)))
+    assert general
+    check_parity(d2, opts=orc.Opts(comment="#"))  # strict: the first bare quote is the error, rows before it delivered
+    # TrimLeadingSpace with a delimiter that is itself white space eats empty fields: general path
+    d3 = b"a\tb\tc\n1\t\t3\n \t4\t5\t6\n"
+    (_, general) = _route(lambda: check_parity(d3, opts=orc.Opts(comma="\t", trim_leading_space=True, fields_per_record=-1)))
+    assert general
+
+
 # ------------------------------------------------------------------ multi-byte reader runes (csrc/subst.cu)
 UNISPACES = ["\u0085", "\u00a0", "\u1680", "\u2000", "\u2005", "\u200a", "\u2028", "\u2029", "\u202f", "\u205f", "\u3000"]
 
