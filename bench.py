@@ -307,8 +307,8 @@ def main():
     ap.add_argument("--ref-products", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-batches", type=int, default=16)
-    ap.add_argument("--e2e-workers", type=int, default=4)
+    ap.add_argument("--e2e-batches", type=int, default=24)
+    ap.add_argument("--e2e-workers", type=int, default=8)
     ap.add_argument("--e2e-sweep", default="", help="e.g. 8x4,16x8: time these (batches x workers) settings of the e2e leg, report the best")
     args = ap.parse_args()
     ORD_ROWS, CUST_ROWS, PROD_ROWS, PEOPLE_ROWS, INDEX_ROWS = args.orders, args.customers, args.products, args.people, args.index_rows
@@ -344,6 +344,12 @@ def main():
     d_orders = ctx.gen_csv("orders", (rank * ORD_ROWS, (rank + 1) * ORD_ROWS), seed=SEED, n_cust=CUST_ROWS, n_prod=PROD_ROWS, header=True)
     d_people = ctx.gen_csv("people", (rank * PEOPLE_ROWS, (rank + 1) * PEOPLE_ROWS), seed=SEED, header=True)
     ctx.sync()
+    # the step's tables, index structures and scratch (~35 GB at the default sizes, more with the gathered build side) come
+    # out of memory the pool maps once, here, instead of growing it over the first iterations (measured at N = 2 without
+    # it: steps of 200 ms until the sixth iteration, 56 ms after)
+    free_b, _total_b = torch.cuda.mem_get_info(local)
+    reserve_b = int(min(0.45 * free_b, 56e9))
+    reserved = ctx.reserve(reserve_b)
 
     # Python's cyclic collector: a full collection walks every object torch's import created (hundreds of ms) and its
     # schedule depends only on allocation counts, so it hits every rank at the same step (measured at N = 2: steps of
@@ -761,7 +767,7 @@ def main():
             "metric": "rows/sec end-to-end Join", "value": world * ORD_ROWS / (ms_join * 1e-3), "unit": "rows/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_join, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(world),
+            "config": dict(workload_config(world), pool_reserved_bytes=reserve_b if reserved else 0),
             "clocks": clocks, "gpu_launches": launches, "out_rows_per_gpu": out_rows,
             "kernel_ms_per_step": kernel_ms / args.steps, "host_gap_ms_per_step": ms_join - kernel_ms / args.steps,
             "host_syncs_per_step": join_syncs, "per_step_ms_rank0": join_per_step,

@@ -42,7 +42,7 @@ class KStat(C.Structure):
 
 # every symbol include/csvplus_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "cpb_abi_version", "cpb_init", "cpb_shutdown", "cpb_ctx_stream", "cpb_sync", "cpb_last_error",
+    "cpb_abi_version", "cpb_init", "cpb_shutdown", "cpb_ctx_stream", "cpb_sync", "cpb_pool_reserve", "cpb_last_error",
     "cpb_host_alloc", "cpb_host_free", "cpb_device_alloc", "cpb_device_free", "cpb_memcpy_h2d", "cpb_memcpy_d2h",
     "cpb_parse_csv", "cpb_csv_quote_parity", "cpb_parse_csv_shard", "cpb_table_col_field", "cpb_table_record_fields",
     "cpb_table_num_rows", "cpb_table_num_cols", "cpb_table_col_name", "cpb_table_find_col", "cpb_table_col_bytes",
@@ -76,6 +76,7 @@ def load():
         "cpb_shutdown": (None, [vp]),
         "cpb_ctx_stream": (vp, [vp]),
         "cpb_sync": (i32, [vp]),
+        "cpb_pool_reserve": (i32, [vp, u64]),
         "cpb_last_error": (C.c_char_p, [vp]),
         "cpb_host_alloc": (i32, [vp, u64, P(vp)]),
         "cpb_host_free": (i32, [vp, vp]),

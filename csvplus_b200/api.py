@@ -134,6 +134,10 @@ class Context:
     def sync(self):
         self.lib.cpb_sync(self.h)
 
+    def reserve(self, nbytes: int) -> bool:
+        """cpb_pool_reserve: map `nbytes` of device memory into this context's pool ahead of time (False: not available)"""
+        return self.lib.cpb_pool_reserve(self.h, int(nbytes)) == 0
+
     @property
     def stream(self) -> int:
         return self.lib.cpb_ctx_stream(self.h) or 0

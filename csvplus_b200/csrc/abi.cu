@@ -219,6 +219,19 @@ int cpb_sync(cpb_ctx* h) {
     CPB_CATCH(c, nullptr)
 }
 
+int cpb_pool_reserve(cpb_ctx* h, uint64_t nbytes) {
+    if (!h) return CPB_ERR_ARG;
+    Ctx* c = &h->c; DeviceGuard g(c);
+    CPB_TRY(c, nullptr)
+    if (nbytes == 0) return CPB_OK;
+    void* p = nullptr;
+    CPB_CUDA(cudaMallocAsync(&p, nbytes, c->pool, c->stream));
+    CPB_CUDA(cudaFreeAsync(p, c->stream));
+    sync_stream(c);
+    return CPB_OK;
+    CPB_CATCH(c, nullptr)
+}
+
 int cpb_host_alloc(cpb_ctx* h, uint64_t n, void** out) {
     Ctx* c = &h->c; DeviceGuard g(c);
     CPB_TRY(c, nullptr)

@@ -60,6 +60,15 @@ func NewContext(device int) (*Context, error) {
 	return c, nil
 }
 
+// Reserve maps nbytes of device memory into the context's pool ahead of time (cpb_pool_reserve), so that a steady loop
+// of parses and joins never waits for the driver to map pages.  Optional.
+func (c *Context) Reserve(nbytes uint64) error {
+	if st := C.cpb_pool_reserve(c.h, C.uint64_t(nbytes)); st != C.CPB_OK {
+		return fmt.Errorf("csvplus: cpb_pool_reserve(%d) failed with status %d", nbytes, int(st))
+	}
+	return nil
+}
+
 // Close releases the context; tables and indices created by it must be closed first.
 func (c *Context) Close() {
 	if c.h != nil {

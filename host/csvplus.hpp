@@ -51,6 +51,9 @@ struct Strs {
 };
 }  // namespace detail
 
+// maps nbytes of device memory into the context's pool ahead of time (cpb_pool_reserve); optional
+inline void Reserve(uint64_t nbytes) { if (cpb_pool_reserve(detail::ctx(), nbytes) != CPB_OK) throw Error(cpb_last_error(detail::ctx())); }
+
 // ---------------------------------------------------------------- predicates (csvplus.go:1243-1293)
 struct Predicate {
     int op = -1;  // CPB_PRED_*; -1 = opaque host function

@@ -119,6 +119,11 @@ int cpb_init(int device, cpb_ctx** out);
 void cpb_shutdown(cpb_ctx* ctx);
 void* cpb_ctx_stream(cpb_ctx* ctx); /* the ctx's cudaStream_t (for event timing by the caller) */
 int cpb_sync(cpb_ctx* ctx);
+/* Maps `nbytes` of device memory into the ctx's pool ahead of time (one allocation + release; the pool keeps what it
+ * maps).  Tables, indices and scratch of later calls are then carved out of memory the pool already holds: no call in a
+ * steady loop waits for the driver to map pages.  Optional — the pool grows on demand without it (and then the first
+ * iterations of a loop pay for the growth).  There is no counterpart in csvplus.go (Go's heap grows the same way). */
+int cpb_pool_reserve(cpb_ctx* ctx, uint64_t nbytes);
 const char* cpb_last_error(cpb_ctx* ctx); /* last CUDA / argument error text of this ctx */
 
 /* Staging memory.  Host: pinned, the Go side fills it with io.ReadFull (replaces the 4 KB bufio reads
