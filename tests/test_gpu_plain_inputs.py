@@ -109,3 +109,21 @@ def test_bench_shapes_vs_oracle():
         t, err = cp.parse_csv(ctx, buf, spec=[(c, -1) for c in spec])
         assert err is None
         assert_table_equals_oracle(t, orc.reader_rows(buf.to_host(), select=spec))
+
+
+def test_pool_reserve_then_parse():
+    """cpb_pool_reserve maps pool memory ahead of time (bench.py reserves its working set); results are unaffected"""
+    import csvplus_b200 as cp
+    from tests.helpers import people_csv
+    ctx = cp.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    try:
+        assert ctx.reserve(256 << 20)
+        assert ctx.reserve(0)
+        data = people_csv(5000)
+        t, err = cp.parse_csv(ctx, data, spec=[("name", -1), ("id", -1)])
+        assert err is None and len(t) == 5000
+        orows = orc.reader_rows(data, orc.Opts(), select=["name", "id"])
+        assert_table_equals_oracle(t, orows)
+        del t
+    finally:
+        ctx.close()
