@@ -224,7 +224,10 @@ class _PendingGather:
 
 def allgather_table_async(ctx, table, dist, group=None):
     """starts the all-gather of `table`'s rows (one size exchange + one collective for all columns) and returns a
-    handle; the caller may run other GPU work (e.g. parse its probe shard) before handle.wait()"""
+    handle; the caller may run other GPU work (e.g. parse its probe shard) before handle.wait().
+    (torch.distributed plumbing of round 1, kept as a cross-check of allgather_table_nccl.  It ships whole column buffers:
+    a row-range view whose first offset is not 0 — Top/Drop/Find results — is refused by cpb_table_from_device
+    ("imported offsets must start at 0"); the library's all-gather, allgather_table_nccl, takes views.)"""
     import torch
     cols = table.columns
     n = len(table)
