@@ -1,5 +1,9 @@
-// parse_general.cu — the general reader path: CommentChar / LazyQuotes / TrimLeadingSpace
+// parse_general.cu — the general (multi-pass) reader path for CommentChar / LazyQuotes / TrimLeadingSpace
 // (csvplus.go:976-993 -> encoding/csv Reader.Comment / LazyQuotes / TrimLeadingSpace).
+//
+// Since round 2 this is the FALLBACK: parse.cu first lets the single-pass scan stand in for it and comes
+// here only when the input needs it — a quote inside a comment line, a real lazy quote, TrimLeadingSpace with a
+// white-space delimiter, stand-in bytes of multi-byte runes (subst.cu) — or when CPB_GENERAL_PATH=dfa asks for it.
 //
 // With these options "inside a quoted field" is no longer the parity of the quote bytes (a comment line
 // may contain quotes, lazy quotes are literal), so record boundaries come from a small byte-level DFA
@@ -8,11 +12,11 @@
 //   g_block_vec    one vector per block of 256 chunks;  g_chain: the true state at every block start
 //   g_chunk_state  the true state at every chunk start
 //   g_count/g_emit record starts per chunk -> exclusive scan -> start positions (uint64)
-//   g_rec_count    one thread per record: the exact sequential machine (options aware) -> lengths, Like terms, errors
+//   g_rec_count    one thread per record: the exact sequential machine (options aware; seq_parse_record_gen lives in
+//                  parse_kernels.cuh, the scan's guarded instantiations use it too) -> lengths, Like terms, errors
 //   g_rec_emit     offsets + unescaped field bytes
-// Exact sizes are known before anything is written (multi-pass: this path trades bandwidth for generality;
-// the default options take the single-pass csv_scan kernel).  Limits: single-byte (ASCII) delimiter and
-// comment characters; TrimLeadingSpace trims ASCII white space (Go also trims the multi-byte Unicode spaces).
+// Exact sizes are known before anything is written (multi-pass: this path trades bandwidth for generality: ≈ 44 GB/s).
+// Delimiter / comment are single bytes here: multi-byte runes and the multi-byte Unicode spaces arrive as stand-in bytes.
 #include <algorithm>
 
 #include "core.hpp"
