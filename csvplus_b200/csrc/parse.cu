@@ -10,10 +10,13 @@
 // shared memory with one bulk-async copy (TMA 1-D, cp.async.bulk + mbarrier).  Bytes are classified
 // with SWAR compares into newline / delimiter bitmaps; quote parity and the running
 // (records, rows, bytes-per-column) totals are carried across tiles by two decoupled look-back
-// chains.  Every thread owns the records that *start* in its 128-byte slice: pass 1 counts,
-// a block scan + look-back turns counts into global output positions, pass 2 writes offsets and
-// gathers field bytes.  Records containing quotes (or running past the staged window) take an exact
-// sequential state machine that restates Go's readRecord byte for byte.
+// chains.  The set bits of the structural bitmap are expanded into a flat index, so that field j of
+// line i is found in O(1); one thread per line counts (pass 1), a block scan + look-back turns counts
+// into global output positions, pass 2 writes offsets and gathers field bytes through a staging buffer
+// into aligned 16-byte stores.  Records containing quotes (or running past the staged window) take an
+// exact sequential state machine that restates Go's readRecord byte for byte.  CommentChar /
+// LazyQuotes / TrimLeadingSpace ride on the same scan whenever the input allows;
+// parse_general.cu is their multi-pass fallback.
 #include <algorithm>
 #include <functional>
 #include <mutex>
